@@ -1,0 +1,145 @@
+/*
+ * msda_b200.h -- C ABI of the B200-native multi-scale deformable attention operator.
+ *
+ * This is the drop-in boundary for the one hot path this repository rebuilds: the
+ * MSDeformAttn operator of On-JungWoan/UVHand (reference tree: models/ops).  Plain pointers
+ * and sizes only; no torch types.  Built as uvhand_b200/lib/libmsda_b200.so for sm_100a.
+ *
+ * Every entry point names the reference interface it replaces (paths relative to
+ * /root/reference).  Tensor layouts are the reference's:
+ *
+ *   value            [N, S, M, D]        S = sum_l H_l*W_l value tokens, M heads, D channels/head
+ *   spatial_shapes   [L, 2] int64        (H_l, W_l)                       -- DEVICE memory
+ *   level_start      [L]    int64        exclusive cumsum of H_l*W_l      -- DEVICE memory
+ *   sampling_loc     [N, Lq, M, L, P, 2] (x, y) normalised to [0,1]; may lie outside
+ *   attn_weight      [N, Lq, M, L, P]
+ *   output           [N, Lq, M, D]       (the reference returns this viewed as [N, Lq, M*D])
+ *   grad_*           same shapes as the tensors they belong to
+ *
+ * Return value: 0 on success, a positive cudaError_t if the CUDA runtime reported one
+ * (the reference only printf()s launch errors, ms_deform_im2col_cuda.cuh:948-952; this ABI
+ * returns them), or a negative MSDA_ERR_* code for a rejected argument.  All launches are
+ * asynchronous on `stream` (a cudaStream_t passed as void*; NULL = the legacy default stream).
+ * There is no CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef MSDA_B200_H_
+#define MSDA_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSDA_B200_ABI_VERSION 1
+
+#define MSDA_OK 0
+#define MSDA_ERR_NULL_POINTER (-1)  /* a required pointer is NULL                                  */
+#define MSDA_ERR_BAD_DIMS (-2)      /* a dimension is negative, or a product overflows the kernel's index range */
+#define MSDA_ERR_IM2COL_STEP (-3)   /* batch % min(batch, im2col_step) != 0  (ms_deform_attn_cuda.cu:50-52) */
+#define MSDA_ERR_UNSUPPORTED (-4)   /* combination not built (e.g. bf16 value with D != 32)        */
+#define MSDA_ERR_MISALIGNED (-5)    /* pointer not aligned to its element size                     */
+#define MSDA_ERR_NO_DEVICE (-6)     /* no usable CUDA device                                       */
+#define MSDA_ERR_BAD_OPTION (-7)    /* msda_b200_set_option: unknown key or value                  */
+
+int msda_b200_abi_version(void);
+/* Static string for any return code of this library (CUDA codes via cudaGetErrorString). */
+const char *msda_b200_strerror(int rc);
+
+/* The reference's chunking precondition, ms_deform_attn_cuda.cu:50-52 and :117-119:
+ * im2col_step_ = min(batch, im2col_step); batch % im2col_step_ must be 0.  The kernels here
+ * process the whole batch in one launch (results do not depend on the chunking), but callers
+ * keep the argument and its error.  Returns MSDA_OK or MSDA_ERR_IM2COL_STEP. */
+int msda_b200_check_im2col_step(int batch, int im2col_step);
+
+/* ---- forward ---------------------------------------------------------------------------
+ * Replaces ms_deformable_im2col_cuda<scalar_t>  (src/cuda/ms_deform_im2col_cuda.cuh:923-954)
+ * and the kernel it launches, ms_deformable_im2col_gpu_kernel (cuh:237-299).  `output` is
+ * fully written (no pre-zeroing needed; the reference zero-fills it first, .cu:54). */
+int msda_fwd_f32(const float *value, const int64_t *spatial_shapes, const int64_t *level_start,
+                 const float *sampling_loc, const float *attn_weight,
+                 int batch, int spatial_size, int num_heads, int channels, int num_levels,
+                 int num_query, int num_point, float *output, void *stream);
+int msda_fwd_f64(const double *value, const int64_t *spatial_shapes, const int64_t *level_start,
+                 const double *sampling_loc, const double *attn_weight,
+                 int batch, int spatial_size, int num_heads, int channels, int num_levels,
+                 int num_query, int num_point, double *output, void *stream);
+/* bf16 value (storage: raw bf16 bits), fp32 locations / weights / output.  channels must be 32.
+ * No reference analogue (the reference dispatches float and double only, .cu:64). */
+int msda_fwd_bf16(const uint16_t *value, const int64_t *spatial_shapes, const int64_t *level_start,
+                  const float *sampling_loc, const float *attn_weight,
+                  int batch, int spatial_size, int num_heads, int channels, int num_levels,
+                  int num_query, int num_point, float *output, void *stream);
+
+/* ---- backward --------------------------------------------------------------------------
+ * Replaces ms_deformable_col2im_cuda<scalar_t> (cuh:956-1327) and its six kernels
+ * (cuh:301-920).  grad_value is ACCUMULATED into and must be zero on entry (the reference
+ * host code zero-fills it, .cu:121); grad_sampling_loc and grad_attn_weight are fully written. */
+int msda_bwd_f32(const float *grad_output, const float *value, const int64_t *spatial_shapes,
+                 const int64_t *level_start, const float *sampling_loc, const float *attn_weight,
+                 int batch, int spatial_size, int num_heads, int channels, int num_levels,
+                 int num_query, int num_point,
+                 float *grad_value, float *grad_sampling_loc, float *grad_attn_weight, void *stream);
+int msda_bwd_f64(const double *grad_output, const double *value, const int64_t *spatial_shapes,
+                 const int64_t *level_start, const double *sampling_loc, const double *attn_weight,
+                 int batch, int spatial_size, int num_heads, int channels, int num_levels,
+                 int num_query, int num_point,
+                 double *grad_value, double *grad_sampling_loc, double *grad_attn_weight, void *stream);
+/* bf16 value and bf16 grad_value (accumulated with red.global.add.noftz.bf16x2), rest fp32. */
+int msda_bwd_bf16(const float *grad_output, const uint16_t *value, const int64_t *spatial_shapes,
+                  const int64_t *level_start, const float *sampling_loc, const float *attn_weight,
+                  int batch, int spatial_size, int num_heads, int channels, int num_levels,
+                  int num_query, int num_point,
+                  uint16_t *grad_value, float *grad_sampling_loc, float *grad_attn_weight, void *stream);
+
+/* ---- parity probe ----------------------------------------------------------------------
+ * Dumps, for every (n, q, m, l, p), what the kernels' shared sample-geometry routine decides:
+ * floor of the pixel coordinate and the corner mask (bit0..3 = corner v1..v4 inside the level,
+ * bit4 = sample accepted by the coarse test of cuh:288).  Rejected samples report 0/0/0.
+ * This is how "indices bit-exact" is checked on the device; it runs the same __device__
+ * function the forward and backward kernels inline. */
+int msda_sample_index_f32(const int64_t *spatial_shapes, const float *sampling_loc,
+                          int batch, int num_query, int num_heads, int num_levels, int num_point,
+                          int32_t *h_low, int32_t *w_low, uint8_t *mask, void *stream);
+
+/* ---- host-buffer entry points (what a non-torch caller binds) ---------------------------
+ * All pointers are HOST memory (pinned or pageable).  The call copies inputs to the device,
+ * runs forward (and backward), copies results back and returns when they are in place.
+ * A plan owns the device buffers, pinned staging and streams for one problem size; create it
+ * once and reuse it.  These wrap the same device entry points as above. */
+typedef struct msda_host_plan msda_host_plan;
+
+int msda_host_plan_create(msda_host_plan **plan, int device,
+                          int batch, int spatial_size, int num_heads, int channels,
+                          int num_levels, int num_query, int num_point);
+void msda_host_plan_destroy(msda_host_plan *plan);
+/* Bytes moved host->device and device->host by one msda_host_fwd_bwd_f32 call. */
+int msda_host_plan_traffic(const msda_host_plan *plan, int64_t *h2d_bytes, int64_t *d2h_bytes);
+/* Pin / unpin a caller buffer so the copies can run asynchronously at full PCIe rate. */
+int msda_host_register(void *ptr, int64_t bytes);
+int msda_host_unregister(void *ptr);
+
+int msda_host_fwd_f32(msda_host_plan *plan, const float *value, const int64_t *spatial_shapes,
+                      const int64_t *level_start, const float *sampling_loc,
+                      const float *attn_weight, float *output);
+int msda_host_fwd_bwd_f32(msda_host_plan *plan, const float *value, const int64_t *spatial_shapes,
+                          const int64_t *level_start, const float *sampling_loc,
+                          const float *attn_weight, const float *grad_output, float *output,
+                          float *grad_value, float *grad_sampling_loc, float *grad_attn_weight);
+
+/* ---- tuning / introspection --------------------------------------------------------------
+ * Keys: "fwd_path", "bwd_path": 0 = automatic, 1 = force the any-shape kernels,
+ * 2.. = a specific specialised variant.  Used by bench.py and the tests to
+ * exercise every kernel on the same inputs.  Returns MSDA_OK or MSDA_ERR_BAD_OPTION. */
+int msda_b200_set_option(const char *key, int value);
+int msda_b200_get_option(const char *key, int *value);
+/* Number of kernels this library has launched since load (all streams); bench.py's
+ * gpu_launches claim is read from here. */
+int64_t msda_b200_launch_count(void);
+/* Name of the kernel family the last forward / backward call dispatched to. */
+const char *msda_b200_last_path(int backward);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSDA_B200_H_ */

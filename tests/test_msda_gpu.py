@@ -1,0 +1,600 @@
+"""GPU parity tests (run with -m gpu on the B200 box).  Everything here calls the product through
+the C ABI (ctypes on libmsda_b200.so) or through the reference-facing extension / autograd
+Function, and scores it against the CPU oracle (oracle/) or the committed golden vectors.
+
+Tolerances (BASELINE.json north_star): integer work bit-exact; fp32 forward rtol 1e-5; fp32
+gradients rtol 1e-4 (atomic ordering); bf16 rtol 1e-2; with atol = rtol * max|reference|.
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import c_oracle
+from uvhand_b200 import cabi
+from uvhand_b200.workloads import WORKLOADS, Workload, make_inputs
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+IDS = [os.path.basename(p)[:-4] for p in GOLDEN]
+
+FWD_RTOL, GRAD_RTOL, BF16_RTOL = 1e-5, 1e-4, 1e-2
+
+
+def close(got, want, rtol):
+    got = np.asarray(got, dtype=np.float64)
+    want = np.asarray(want, dtype=np.float64)
+    atol = rtol * max(float(np.abs(want).max()), 1e-30)
+    bad = np.abs(got - want) > atol + rtol * np.abs(want)
+    if bad.any():
+        i = np.unravel_index(np.argmax(np.abs(got - want)), got.shape)
+        raise AssertionError(f"{bad.sum()} / {bad.size} outside rtol={rtol}: worst at {i}: got {got[i]!r} want {want[i]!r}")
+
+
+def dev(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    return t.to(dtype) if dtype is not None else t
+
+
+class Paths:
+    """Context manager forcing a kernel family: 0 auto, 1 any-shape kernels."""
+
+    def __init__(self, fwd=0, bwd=0):
+        self.f, self.b = fwd, bwd
+
+    def __enter__(self):
+        cabi.set_option("fwd_path", self.f)
+        cabi.set_option("bwd_path", self.b)
+
+    def __exit__(self, *a):
+        cabi.set_option("fwd_path", 0)
+        cabi.set_option("bwd_path", 0)
+
+
+def run_cabi(kind, value, shapes, lsi, loc, aw, grad_out=None):
+    """numpy in -> numpy out through msda_fwd_* / msda_bwd_* with device buffers."""
+    tdt = {"f32": torch.float32, "f64": torch.float64, "bf16": torch.float32}[kind]
+    vdt = torch.bfloat16 if kind == "bf16" else tdt
+    v = dev(value, vdt)
+    sh, ls = dev(np.asarray(shapes, np.int64)), dev(np.asarray(lsi, np.int64))
+    lo, a = dev(loc, tdt), dev(aw, tdt)
+    N, S, M, D = v.shape
+    _, Lq, _, L, P, _ = lo.shape
+    dims = (N, S, M, D, L, Lq, P)
+    out = torch.full((N, Lq, M * D), float("nan"), device="cuda", dtype=tdt)
+    st = torch.cuda.current_stream().cuda_stream
+    cabi.forward(kind, v.data_ptr(), sh.data_ptr(), ls.data_ptr(), lo.data_ptr(), a.data_ptr(), dims,
+                 out.data_ptr(), st)
+    res = {"out": out.cpu().numpy(), "fwd_path": cabi.last_path(False)}
+    if grad_out is not None:
+        g = dev(grad_out, tdt).reshape(N, Lq, M * D).contiguous()
+        gv = torch.zeros_like(v)
+        gl = torch.full(lo.shape, float("nan"), device="cuda", dtype=tdt)
+        ga = torch.full(a.shape, float("nan"), device="cuda", dtype=tdt)
+        cabi.backward(kind, g.data_ptr(), v.data_ptr(), sh.data_ptr(), ls.data_ptr(), lo.data_ptr(),
+                      a.data_ptr(), dims, gv.data_ptr(), gl.data_ptr(), ga.data_ptr(), st)
+        res.update(grad_value=gv.float().cpu().numpy() if kind == "bf16" else gv.cpu().numpy(),
+                   grad_loc=gl.cpu().numpy(), grad_aw=ga.cpu().numpy(), bwd_path=cabi.last_path(True))
+    torch.cuda.synchronize()
+    return res
+
+
+def oracle(value, shapes, lsi, loc, aw, grad_out, variant="f32x"):
+    out = c_oracle.forward(value, shapes, lsi, loc, aw, variant)
+    gv, gl, ga = c_oracle.backward(grad_out, value, shapes, lsi, loc, aw, variant)
+    return {"out": out, "grad_value": gv, "grad_loc": gl, "grad_aw": ga}
+
+
+def check_all(res, ref, fwd_rtol=FWD_RTOL, grad_rtol=GRAD_RTOL):
+    close(res["out"], ref["out"], fwd_rtol)
+    close(res["grad_value"], ref["grad_value"], grad_rtol)
+    close(res["grad_loc"], ref["grad_loc"], grad_rtol)
+    close(res["grad_aw"], ref["grad_aw"], grad_rtol)
+
+
+def np_inputs(wl, seed, **kw):
+    t = make_inputs(wl, seed=seed, device="cpu", **kw)
+    return {k: v.numpy() for k, v in t.items()}
+
+
+# ------------------------------------------------------------------------------------------------
+# golden vectors written by the unmodified reference (fp64 grid_sample path + autograd)
+# ------------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("forced", [0, 1], ids=["auto", "anyshape"])
+@pytest.mark.parametrize("path", GOLDEN, ids=IDS)
+def test_golden_f32(path, forced):
+    g = np.load(path)
+    with Paths(forced, forced):
+        res = run_cabi("f32", g["value"], g["shapes"], g["lsi"], g["loc"], g["aw"], g["grad_out"])
+    check_all(res, g)
+    if forced == 0 and g["value"].shape[3] == 32:
+        assert res["fwd_path"] == "fwd_d32_f32" and res["bwd_path"] == "bwd_d32_f32"
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=IDS)
+def test_golden_f64(path):
+    g = np.load(path)
+    res = run_cabi("f64", g["value"], g["shapes"], g["lsi"], g["loc"], g["aw"], g["grad_out"])
+    check_all(res, g, 1e-11, 1e-10)
+
+
+def test_reference_test_anchor():
+    # models/ops/test.py seed-3 forward, 4 d.p.
+    g = np.load(GOLDEN[IDS.index("testpy_n1")])
+    res = run_cabi("f32", g["value"], g["shapes"], g["lsi"], g["loc"], g["aw"])
+    want = np.array([[0.0019, 0.0046, 0.0047, 0.0044], [0.0038, 0.0025, 0.0018, 0.0036]])
+    assert np.allclose(np.round(res["out"][0], 4), want, atol=1e-4)
+
+
+# ------------------------------------------------------------------------------------------------
+# integer work: bit-exact against the oracle
+# ------------------------------------------------------------------------------------------------
+
+def _index_gpu(shapes, loc):
+    sh, lo = dev(np.asarray(shapes, np.int64)), dev(loc, torch.float32)
+    N, Lq, M, L, P, _ = lo.shape
+    h = torch.full((N, Lq, M, L, P), -7, device="cuda", dtype=torch.int32)
+    w = torch.full_like(h, -7)
+    k = torch.full((N, Lq, M, L, P), 255, device="cuda", dtype=torch.uint8)
+    cabi.sample_index(sh.data_ptr(), lo.data_ptr(), N, Lq, M, L, P, h.data_ptr(), w.data_ptr(), k.data_ptr(),
+                      torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    return h.cpu().numpy(), w.cpu().numpy(), k.cpu().numpy()
+
+
+@pytest.mark.parametrize("levels", [WORKLOADS["c2_detr_encoder"].levels, WORKLOADS["c3_arctic_encoder"].levels,
+                                    WORKLOADS["c5_hires"].levels, ((6, 4), (3, 2)), ((1, 1), (1, 7), (9, 1))],
+                         ids=["c2", "c3", "c5", "c1", "degenerate"])
+def test_sample_index_bit_exact(levels):
+    rng = np.random.default_rng(42)
+    shapes = np.array(levels, dtype=np.int64)
+    L = len(levels)
+    parts = [rng.random((1, 4000, 2, L, 4, 2)).astype(np.float32),                    # U[0,1)
+             (rng.random((1, 4000, 2, L, 4, 2)) * 3 - 1).astype(np.float32)]          # U[-1,2)
+    # exact pixel centres, exact pixel edges, half a pixel outside, for every level
+    edge = np.zeros((1, 2048, 2, L, 4, 2), dtype=np.float32)
+    for l, (H, W) in enumerate(levels):
+        k = np.arange(2048 * 2 * 4, dtype=np.float64).reshape(2048, 2, 4)
+        cx = ((k % (W + 2)) - 1 + 0.5) / W
+        cy = (((k // 3) % (H + 2)) - 1 + 0.5) / H
+        ex = (k % (W + 1)) / W
+        ey = ((k // 5) % (H + 1)) / H
+        pick = (k.astype(np.int64) % 2 == 0)
+        edge[0, :, :, l, :, 0] = np.where(pick, cx, ex)
+        edge[0, :, :, l, :, 1] = np.where(pick, cy, ey)
+    parts.append(edge)
+    special = rng.random((1, 64, 2, L, 4, 2)).astype(np.float32)
+    special[0, 0::4, :, :, 0, 0] = np.nan
+    special[0, 1::4, :, :, 1, 1] = np.inf
+    special[0, 2::4, :, :, 2, 0] = -np.inf
+    special[0, 3::4, :, :, 3, 1] = 1e30
+    parts.append(special)
+    for loc in parts:
+        h, w, k = _index_gpu(shapes, loc)
+        h0, w0, k0 = c_oracle.sample_index(shapes, loc, "f32")
+        assert np.array_equal(k, k0)
+        assert np.array_equal(h, h0)
+        assert np.array_equal(w, w0)
+
+
+@pytest.mark.parametrize("forced", [0, 1], ids=["auto", "anyshape"])
+def test_grad_value_touch_pattern_exact(forced):
+    """Which value rows receive gradient is pure index/mask work: the set must match exactly."""
+    wl = Workload("t", 2, ((9, 13), (5, 7), (3, 4), (2, 2)), 60, loc_dist="twostage")
+    x = np_inputs(wl, 7, pad_frac=0.0)
+    x["grad_out"] = np.ones_like(x["grad_out"])
+    with Paths(forced, forced):
+        res = run_cabi("f32", x["value"], x["shapes"], x["lsi"], x["loc"], x["aw"], x["grad_out"])
+    ref = oracle(x["value"], x["shapes"], x["lsi"], x["loc"], x["aw"], x["grad_out"])
+    assert np.array_equal(res["grad_value"] != 0, ref["grad_value"] != 0)
+    # rejected samples give exactly zero location / weight gradients
+    _, _, k = c_oracle.sample_index(x["shapes"], x["loc"], "f32")
+    assert (k == 0).any()
+    assert np.all(res["grad_aw"][k == 0] == 0) and np.all(res["grad_loc"][k == 0] == 0)
+
+
+# ------------------------------------------------------------------------------------------------
+# seeded workloads at sizes the oracle finishes in seconds
+# ------------------------------------------------------------------------------------------------
+
+MID_LEVELS = ((40, 57), (20, 29), (10, 15), (5, 8))
+MID_S = sum(h * w for h, w in MID_LEVELS)
+
+
+@pytest.mark.parametrize("forced", [0, 1], ids=["auto", "anyshape"])
+@pytest.mark.parametrize("dist,Lq", [("encoder", MID_S), ("uniform", 777), ("twostage", 300), ("contended", 512)])
+def test_mid_size_f32(dist, Lq, forced):
+    wl = Workload("mid", 2, MID_LEVELS, Lq, loc_dist=dist)
+    x = np_inputs(wl, 3)
+    with Paths(forced, forced):
+        res = run_cabi("f32", x["value"], x["shapes"], x["lsi"], x["loc"], x["aw"], x["grad_out"])
+    check_all(res, oracle(x["value"], x["shapes"], x["lsi"], x["loc"], x["aw"], x["grad_out"]))
+
+
+@pytest.mark.parametrize("dist,Lq", [("encoder", MID_S), ("twostage", 300)])
+def test_mid_size_bf16(dist, Lq):
+    wl = Workload("mid", 2, MID_LEVELS, Lq, loc_dist=dist)
+    x = np_inputs(wl, 4)
+    v_bf16 = torch.from_numpy(x["value"]).to(torch.bfloat16)
+    v_round = v_bf16.float().numpy()                      # what the kernel actually reads
+    res = run_cabi("bf16", v_round, x["shapes"], x["lsi"], x["loc"], x["aw"], x["grad_out"])
+    ref = oracle(v_round, x["shapes"], x["lsi"], x["loc"], x["aw"], x["grad_out"])
+    assert res["fwd_path"] == "fwd_d32_bf16" and res["bwd_path"] == "bwd_d32_bf16"
+    close(res["out"], ref["out"], FWD_RTOL)               # same rounded inputs -> fp32-level agreement
+    close(res["grad_loc"], ref["grad_loc"], GRAD_RTOL)
+    close(res["grad_aw"], ref["grad_aw"], GRAD_RTOL)
+    close(res["grad_value"], ref["grad_value"], BF16_RTOL * 4 if dist == "encoder" else BF16_RTOL)
+    # and against the unrounded value: the stated bf16 tolerance
+    ref_full = oracle(x["value"], x["shapes"], x["lsi"], x["loc"], x["aw"], x["grad_out"])
+    close(res["out"], ref_full["out"], BF16_RTOL)
+
+
+SHAPES = [
+    # (N, M, D, L, P, Lq, levels)                 what it exercises
+    (1, 1, 1, 1, 1, 1, ((1, 1),)),                # smallest possible
+    (3, 3, 32, 4, 4, 5, ((7, 5), (4, 3), (2, 2), (1, 1))),     # M % 4 != 0: a warp spans queries
+    (2, 8, 32, 3, 2, 9, ((6, 5), (3, 3), (2, 1))),             # L*P = 6: runtime-LP specialised kernel
+    (1, 2, 32, 8, 4, 6, tuple((3, 2) for _ in range(8))),      # L*P = 32: record-buffer limit
+    (1, 2, 32, 5, 7, 6, tuple((3, 2) for _ in range(5))),      # L*P = 35: falls back to any-shape
+    (1, 2, 32, 9, 1, 6, tuple((2, 2) for _ in range(9))),      # L = 9 > 8: any-shape
+    (2, 2, 30, 2, 2, 3, ((6, 4), (3, 2))),        # test.py:85 channel counts
+    (2, 2, 33, 2, 2, 3, ((6, 4), (3, 2))),
+    (1, 2, 64, 2, 2, 3, ((6, 4), (3, 2))),
+    (1, 2, 71, 2, 2, 3, ((6, 4), (3, 2))),
+    (1, 2, 1025, 2, 2, 2, ((6, 4), (3, 2))),
+    (1, 1, 2048, 2, 2, 2, ((6, 4), (3, 2))),
+    (1, 1, 3096, 2, 2, 2, ((6, 4), (3, 2))),
+    (5, 4, 32, 4, 4, 1, ((3, 3), (2, 2), (1, 2), (1, 1))),     # one query
+]
+
+
+@pytest.mark.parametrize("shape", SHAPES, ids=[f"N{s[0]}M{s[1]}D{s[2]}L{s[3]}P{s[4]}Lq{s[5]}" for s in SHAPES])
+@pytest.mark.parametrize("kind", ["f32", "f64"])
+def test_shape_sweep(shape, kind):
+    N, M, D, L, P, Lq, levels = shape
+    wl = Workload("s", N, levels, Lq, M=M, D=D, P=P, loc_dist="twostage")
+    x = np_inputs(wl, 9, pad_frac=0.0, offset_px=1.0)
+    x["loc"] = (x["loc"] * 0.4 + 0.5).astype(np.float32)   # mostly inside, some out
+    res = run_cabi(kind, x["value"], x["shapes"], x["lsi"], x["loc"], x["aw"], x["grad_out"])
+    variant = "f32x" if kind == "f32" else "f64"
+    ref = oracle(x["value"], x["shapes"], x["lsi"], x["loc"], x["aw"], x["grad_out"], variant)
+    if kind == "f32":
+        check_all(res, ref)
+    else:
+        check_all(res, ref, 1e-12, 1e-11)
+
+
+def test_special_locations_contribute_zero():
+    wl = Workload("s", 1, ((4, 5), (2, 3)), 8, M=8, D=32, P=4, loc_dist="uniform")
+    x = np_inputs(wl, 1)
+    loc = x["loc"]
+    loc[0, 0, :, 0, 0] = [np.nan, 0.5]
+    loc[0, 1, :, 1, 1] = [0.5, np.inf]
+    loc[0, 2, :, 0, 2] = [-np.inf, np.nan]
+    loc[0, 3, :, 1, 3] = [7.0, 0.5]
+    for forced in (0, 1):
+        with Paths(forced, forced):
+            res = run_cabi("f32", x["value"], x["shapes"], x["lsi"], loc, x["aw"], x["grad_out"])
+        ref = oracle(x["value"], x["shapes"], x["lsi"], loc, x["aw"], x["grad_out"])
+        for k in ("out", "grad_value", "grad_loc", "grad_aw"):
+            assert np.isfinite(res[k]).all(), k
+        check_all(res, ref)
+        assert np.all(res["grad_loc"][0, 0, :, 0, 0] == 0) and np.all(res["grad_aw"][0, 1, :, 1, 1] == 0)
+
+
+def test_invalid_corners_are_never_read():
+    """Zero padding means 'do not load', not 'load and multiply by zero': an inf in a row that is
+    only ever an out-of-range neighbour must not reach the output (cuh:55-78)."""
+    levels = ((3, 3),)
+    wl = Workload("s", 1, levels, 4, M=8, D=32, P=4, loc_dist="uniform")
+    x = np_inputs(wl, 2, pad_frac=0.0)
+    # all samples in the top-left pixel's upper-left quadrant: h_low = w_low = -1, only corner v4 = (0,0) valid
+    x["loc"][...] = np.float32(0.05)
+    x["value"][0, 1:] = np.inf                      # every row except pixel (0,0)
+    for forced in (0, 1):
+        with Paths(forced, forced):
+            res = run_cabi("f32", x["value"], x["shapes"], x["lsi"], x["loc"], x["aw"], x["grad_out"])
+        assert np.isfinite(res["out"]).all()
+        assert np.isfinite(res["grad_loc"]).all() and np.isfinite(res["grad_aw"]).all()
+        assert np.all(res["grad_value"][0, 1:] == 0)
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE.json full sizes: size-independent properties + oracle on a slice
+# ------------------------------------------------------------------------------------------------
+
+def _full_size(wl, kind="f32", seed=0):
+    t = make_inputs(wl, seed=seed, device="cuda", value_dtype=torch.bfloat16 if kind == "bf16" else torch.float32)
+    dims = wl.dims()
+    st = torch.cuda.current_stream().cuda_stream
+    out = torch.empty(wl.N, wl.Lq, wl.M * wl.D, device="cuda")
+    cabi.forward(kind, t["value"].data_ptr(), t["shapes"].data_ptr(), t["lsi"].data_ptr(), t["loc"].data_ptr(),
+                 t["aw"].data_ptr(), dims, out.data_ptr(), st)
+    gv = torch.zeros_like(t["value"])
+    gl = torch.empty_like(t["loc"])
+    ga = torch.empty_like(t["aw"])
+    cabi.backward(kind, t["grad_out"].data_ptr(), t["value"].data_ptr(), t["shapes"].data_ptr(), t["lsi"].data_ptr(),
+                  t["loc"].data_ptr(), t["aw"].data_ptr(), dims, gv.data_ptr(), gl.data_ptr(), ga.data_ptr(), st)
+    torch.cuda.synchronize()
+    return t, out, gv, gl, ga
+
+
+@pytest.mark.parametrize("name", ["c2_detr_encoder", "c3_arctic_encoder", "c3_arctic_decoder", "c4_dino_decoder",
+                                  "c4_dino_decoder_train"])
+def test_full_size_properties_f32(name):
+    wl = WORKLOADS[name]
+    t, out, gv, gl, ga = _full_size(wl)
+    assert cabi.last_path(False) == "fwd_d32_f32" and cabi.last_path(True) == "bwd_d32_f32"
+    g = t["grad_out"].view_as(out).double()
+    # forward is linear in value and in the weights: <out, g> = <value, grad_value> = <w, grad_w>
+    lhs = float((out.double() * g).sum())
+    rhs_v = float((t["value"].double() * gv.double()).sum())
+    rhs_w = float((t["aw"].double() * ga.double()).sum())
+    scale = float((out.double() * g).abs().sum())
+    assert abs(lhs - rhs_v) < 1e-5 * scale
+    assert abs(lhs - rhs_w) < 1e-5 * scale
+    # oracle on a slice of queries (full value): forward, grad_loc, grad_w for those queries
+    gen = torch.Generator().manual_seed(1)
+    idx = torch.randperm(wl.Lq, generator=gen)[:96].sort().values
+    cpu = {k: v.cpu() for k, v in t.items()}
+    sub_loc = cpu["loc"][:, idx].contiguous().numpy()
+    sub_aw = cpu["aw"][:, idx].contiguous().numpy()
+    sub_g = cpu["grad_out"][:, idx].contiguous().numpy()
+    ref = oracle(cpu["value"].numpy(), cpu["shapes"].numpy(), cpu["lsi"].numpy(), sub_loc, sub_aw, sub_g)
+    close(out.cpu()[:, idx].numpy(), ref["out"], FWD_RTOL)
+    close(gl.cpu()[:, idx].numpy(), ref["grad_loc"], GRAD_RTOL)
+    close(ga.cpu()[:, idx].numpy(), ref["grad_aw"], GRAD_RTOL)
+    # index decisions for the whole tensor, bit-exact
+    h, w, k = _index_gpu(cpu["shapes"].numpy(), cpu["loc"].numpy()[:1, :4096])
+    h0, w0, k0 = c_oracle.sample_index(cpu["shapes"].numpy(), cpu["loc"].numpy()[:1, :4096], "f32")
+    assert np.array_equal(h, h0) and np.array_equal(w, w0) and np.array_equal(k, k0)
+
+
+def test_full_size_c2_grad_value_vs_oracle():
+    """C2 is small enough (5.7 M samples) for the OpenMP oracle to do the whole backward."""
+    wl = WORKLOADS["c2_detr_encoder"]
+    t, out, gv, gl, ga = _full_size(wl, seed=2)
+    cpu = {k: v.cpu().numpy() for k, v in t.items()}
+    ref = oracle(cpu["value"], cpu["shapes"], cpu["lsi"], cpu["loc"], cpu["aw"], cpu["grad_out"])
+    close(out.cpu().numpy(), ref["out"], FWD_RTOL)
+    close(gv.cpu().numpy(), ref["grad_value"], GRAD_RTOL)
+    close(gl.cpu().numpy(), ref["grad_loc"], GRAD_RTOL)
+    close(ga.cpu().numpy(), ref["grad_aw"], GRAD_RTOL)
+
+
+def test_full_size_c5_bf16_properties():
+    wl = WORKLOADS["c5_hires"]
+    t, out, gv, gl, ga = _full_size(wl, kind="bf16")
+    assert cabi.last_path(False) == "fwd_d32_bf16" and cabi.last_path(True) == "bwd_d32_bf16"
+    g = t["grad_out"].view_as(out).double()
+    lhs = float((out.double() * g).sum())
+    rhs_w = float((t["aw"].double() * ga.double()).sum())
+    scale = float((out.double() * g).abs().sum())
+    assert abs(lhs - rhs_w) < 1e-5 * scale
+    rhs_v = float((t["value"].double() * gv.double()).sum())        # bf16-accumulated
+    assert abs(lhs - rhs_v) < 2e-2 * scale
+    gen = torch.Generator().manual_seed(1)
+    idx = torch.randperm(wl.Lq, generator=gen)[:64].sort().values
+    cpu = {k: v.cpu() for k, v in t.items()}
+    v1 = cpu["value"][:1].float().numpy()
+    ref_out = c_oracle.forward(v1, cpu["shapes"].numpy(), cpu["lsi"].numpy(),
+                               cpu["loc"][:1, idx].contiguous().numpy(), cpu["aw"][:1, idx].contiguous().numpy(), "f32x")
+    close(out.cpu()[:1, idx].numpy(), ref_out, FWD_RTOL)
+
+
+# ------------------------------------------------------------------------------------------------
+# the reference-facing layers: extension module, autograd Function, nn.Module
+# ------------------------------------------------------------------------------------------------
+
+def test_function_matches_oracle_and_is_chunk_invariant():
+    from uvhand_b200.functions import MSDeformAttnFunction
+    wl = Workload("f", 6, ((9, 13), (5, 7), (3, 4), (2, 2)), 50, loc_dist="twostage")
+    x = make_inputs(wl, seed=21, device="cpu")
+    ref = oracle(*[x[k].numpy() for k in ("value", "shapes", "lsi", "loc", "aw", "grad_out")])
+    outs = []
+    for step in (64, 6, 3, 2, 1):
+        v = x["value"].cuda().requires_grad_(True)
+        lo = x["loc"].cuda().requires_grad_(True)
+        a = x["aw"].cuda().requires_grad_(True)
+        out = MSDeformAttnFunction.apply(v, x["shapes"].cuda(), x["lsi"].cuda(), lo, a, step)
+        assert out.shape == (wl.N, wl.Lq, wl.M * wl.D) and out.is_contiguous()
+        out.backward(x["grad_out"].cuda())
+        close(out.detach().cpu().numpy(), ref["out"], FWD_RTOL)
+        close(v.grad.cpu().numpy(), ref["grad_value"], GRAD_RTOL)
+        close(lo.grad.cpu().numpy(), ref["grad_loc"], GRAD_RTOL)
+        close(a.grad.cpu().numpy(), ref["grad_aw"], GRAD_RTOL)
+        outs.append(out.detach())
+    for o in outs[1:]:
+        assert torch.equal(o, outs[0])       # forward is deterministic and independent of im2col_step
+    # ms_deform_attn_cuda.cu:52: batch 6, im2col_step 4 -> error
+    with pytest.raises(RuntimeError, match="must divide im2col_step"):
+        MSDeformAttnFunction.apply(x["value"].cuda(), x["shapes"].cuda(), x["lsi"].cuda(), x["loc"].cuda(),
+                                   x["aw"].cuda(), 4)
+
+
+def test_function_dtype_policy():
+    from uvhand_b200.functions import MSDeformAttnFunction
+    from uvhand_b200.functions import ms_deform_attn_func as F
+    wl = Workload("f", 2, ((6, 4), (3, 2)), 5, M=8, D=32, P=4, loc_dist="uniform")
+    x = make_inputs(wl, seed=22, device="cuda")
+    args = (x["shapes"], x["lsi"], x["loc"], x["aw"], 64)
+    base = MSDeformAttnFunction.apply(x["value"], *args)
+    # models/ops casts every value to float32 (func.py:26): half / bf16 values behave that way by default
+    v16 = x["value"].half()
+    out16 = MSDeformAttnFunction.apply(v16, *args)
+    assert out16.dtype == torch.float32
+    assert torch.allclose(out16, MSDeformAttnFunction.apply(v16.float(), *args), rtol=0, atol=0)
+    vb = x["value"].bfloat16().requires_grad_(True)
+    assert not F.get_bf16_value_mode()
+    out_b = MSDeformAttnFunction.apply(vb, *args)
+    assert cabi.last_path(False) == "fwd_d32_f32"
+    F.set_bf16_value_mode(True)
+    try:
+        out_n = MSDeformAttnFunction.apply(vb, *args)
+        assert cabi.last_path(False) == "fwd_d32_bf16"
+        assert torch.allclose(out_n, out_b, rtol=1e-5, atol=1e-5)
+        out_n.backward(x["grad_out"])
+        assert vb.grad.dtype == torch.bfloat16 and cabi.last_path(True) == "bwd_d32_bf16"
+    finally:
+        F.set_bf16_value_mode(False)
+    assert torch.allclose(out_b, base, rtol=2e-2, atol=2e-2)
+    # float64 all the way (what models/dino/ops permits and test.py's double checks need)
+    out64 = MSDeformAttnFunction.apply(x["value"].double(), x["shapes"], x["lsi"], x["loc"].double(),
+                                       x["aw"].double(), 64)
+    assert out64.dtype == torch.float64 and torch.allclose(out64.float(), base, rtol=1e-5, atol=1e-6)
+
+
+def test_extension_preconditions_raise_like_the_reference():
+    import uvhand_b200
+    M = uvhand_b200.load_extension()
+    wl = Workload("f", 2, ((6, 4), (3, 2)), 5, M=2, D=4, P=2, loc_dist="uniform")
+    x = make_inputs(wl, seed=23, device="cuda")
+    v, sh, ls, lo, a = x["value"], x["shapes"], x["lsi"], x["loc"], x["aw"]
+    M.ms_deform_attn_forward(v, sh, ls, lo, a, 64)
+    with pytest.raises(RuntimeError, match="value tensor has to be contiguous"):
+        M.ms_deform_attn_forward(v.transpose(1, 2).contiguous().transpose(1, 2), sh, ls, lo, a, 64)
+    with pytest.raises(RuntimeError, match="sampling_loc tensor has to be contiguous"):
+        M.ms_deform_attn_forward(v, sh, ls, lo.flip(-1).transpose(1, 2).contiguous().transpose(1, 2), a, 64)
+    with pytest.raises(RuntimeError, match="spatial_shapes must be a CUDA tensor"):
+        M.ms_deform_attn_forward(v, sh.cpu(), ls, lo, a, 64)
+    with pytest.raises(RuntimeError, match="Not implemented on the CPU"):
+        M.ms_deform_attn_forward(v.cpu(), sh, ls, lo, a, 64)
+    with pytest.raises(RuntimeError, match="dtype"):
+        M.ms_deform_attn_forward(v, sh, ls, lo.double(), a, 64)
+    with pytest.raises(RuntimeError, match="int64"):
+        M.ms_deform_attn_forward(v, sh.int(), ls, lo, a, 64)
+    with pytest.raises(RuntimeError, match="not implemented for"):
+        M.ms_deform_attn_forward(v.half(), sh, ls, lo.half(), a.half(), 64)
+    with pytest.raises(RuntimeError, match="grad_output tensor has to be contiguous"):
+        g = torch.randn(2, 8, 5, device="cuda").transpose(1, 2)
+        M.ms_deform_attn_backward(v, sh, ls, lo, a, g, 64)
+    res = M.ms_deform_attn_backward(v, sh, ls, lo, a, torch.randn(2, 5, 8, device="cuda"), 64)
+    assert isinstance(res, list) and [tuple(r.shape) for r in res] == [tuple(v.shape), tuple(lo.shape), tuple(a.shape)]
+
+
+@pytest.mark.parametrize("channels", [30, 32, 64, 71])
+def test_gradcheck_like_reference_test(channels):
+    """models/ops/test.py:63-78: torch.autograd.gradcheck in float64 at the test's shape."""
+    from uvhand_b200.functions import MSDeformAttnFunction
+    torch.manual_seed(3)
+    N, M, Lq, L, P = 1, 2, 2, 2, 2
+    shapes = torch.as_tensor([(6, 4), (3, 2)], dtype=torch.long).cuda()
+    lsi = torch.cat((shapes.new_zeros((1,)), shapes.prod(1).cumsum(0)[:-1]))
+    S = 30
+    value = (torch.rand(N, S, M, channels) * 0.01).cuda().double().requires_grad_(True)
+    loc = torch.rand(N, Lq, M, L, P, 2).cuda().double().requires_grad_(True)
+    aw = torch.rand(N, Lq, M, L, P).cuda() + 1e-5
+    aw = (aw / aw.sum(-1, keepdim=True).sum(-2, keepdim=True)).double().requires_grad_(True)
+    assert torch.autograd.gradcheck(MSDeformAttnFunction.apply, (value, shapes, lsi, loc, aw, 2))
+
+
+@pytest.mark.parametrize("ref_dim", [2, 42, 4])
+def test_module_against_grid_sample_port(ref_dim):
+    """MSDeformAttn end to end (projections + op) against the same module with the op replaced by the
+    port of the reference's CPU path."""
+    from oracle.grid_sample_port import msda_grid_sample
+    from uvhand_b200.modules import MSDeformAttn
+    torch.manual_seed(5)
+    levels = ((12, 17), (6, 9), (3, 5), (2, 3))
+    shapes = torch.as_tensor(levels, dtype=torch.long).cuda()
+    lsi = torch.cat((shapes.new_zeros((1,)), shapes.prod(1).cumsum(0)[:-1]))
+    S = int(shapes.prod(1).sum())
+    N, Lq = 2, 37
+    mod = MSDeformAttn(256, 4, 8, 4).cuda()
+    with torch.no_grad():
+        mod.sampling_offsets.weight.normal_(0, 0.02)
+        mod.attention_weights.weight.normal_(0, 0.1)
+    query = torch.randn(N, Lq, 256, device="cuda", requires_grad=True)
+    feat = torch.randn(N, S, 256, device="cuda", requires_grad=True)
+    refp = torch.rand(N, Lq, 4, ref_dim, device="cuda")
+    if ref_dim == 4:
+        refp[..., 2:] *= 0.3
+    pad = torch.zeros(N, S, dtype=torch.bool, device="cuda")
+    pad[:, -5:] = True
+    out = mod(query, refp, feat, shapes, lsi, pad)
+    out.sum().backward()
+    gq, gf = query.grad.clone(), feat.grad.clone()
+    query.grad = feat.grad = None
+
+    # same module arithmetic, op swapped for the grid_sample port
+    value = mod.value_proj(feat).masked_fill(pad[..., None], 0.0).view(N, S, 8, 32)
+    off = mod.sampling_offsets(query).view(N, Lq, 8, 4, 4, 2)
+    w = torch.softmax(mod.attention_weights(query).view(N, Lq, 8, 16), -1).view(N, Lq, 8, 4, 4)
+    loc = MSDeformAttn._sampling_locations(refp, off, shapes)
+    out2 = mod.output_proj(msda_grid_sample(value, levels, loc, w))
+    out2.sum().backward()
+    assert torch.allclose(out, out2, rtol=1e-4, atol=1e-5)
+    assert torch.allclose(gq, query.grad, rtol=1e-3, atol=1e-5)
+    assert torch.allclose(gf, feat.grad, rtol=1e-3, atol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------------
+# host-buffer C ABI (what a non-torch caller binds)
+# ------------------------------------------------------------------------------------------------
+
+def test_host_plan_round_trip():
+    wl = Workload("h", 2, ((20, 27), (10, 14), (5, 7), (3, 4)), 333, loc_dist="twostage")
+    x = np_inputs(wl, 31)
+    plan = cabi.HostPlan(*wl.dims())
+    out = np.full((wl.N, wl.Lq, wl.M * wl.D), np.nan, np.float32)
+    gv = np.full(x["value"].shape, np.nan, np.float32)
+    gl = np.full(x["loc"].shape, np.nan, np.float32)
+    ga = np.full(x["aw"].shape, np.nan, np.float32)
+    plan.forward_backward(x["value"], x["shapes"], x["lsi"], x["loc"], x["aw"], x["grad_out"], out, gv, gl, ga)
+    ref = oracle(x["value"], x["shapes"], x["lsi"], x["loc"], x["aw"], x["grad_out"])
+    check_all({"out": out, "grad_value": gv, "grad_loc": gl, "grad_aw": ga}, ref)
+    out2 = np.empty_like(out)
+    plan.forward(x["value"], x["shapes"], x["lsi"], x["loc"], x["aw"], out2)
+    assert np.array_equal(out, out2)
+    # second call must not accumulate into stale grad_value
+    plan.forward_backward(x["value"], x["shapes"], x["lsi"], x["loc"], x["aw"], x["grad_out"], out, gv, gl, ga)
+    close(gv, ref["grad_value"], GRAD_RTOL)
+    h2d, d2h = plan.traffic()
+    assert h2d >= x["value"].nbytes + x["loc"].nbytes + x["aw"].nbytes + x["grad_out"].nbytes
+    assert d2h == out.nbytes + gv.nbytes + gl.nbytes + ga.nbytes
+    plan.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# the reference's own CUDA kernels, recompiled (oracle/_ref), as a second oracle
+# ------------------------------------------------------------------------------------------------
+
+def _ref_cuda():
+    import ctypes
+    p = os.path.join(os.path.dirname(os.path.dirname(__file__)), "oracle", "_ref", "libmsda_refcuda.so")
+    if not os.path.exists(p):
+        pytest.skip("oracle/_ref/libmsda_refcuda.so not built (needs /root/reference at build time)")
+    return ctypes.CDLL(p)
+
+
+@pytest.mark.parametrize("dist,Lq", [("encoder", MID_S), ("twostage", 300)])
+def test_against_reference_cuda_kernels(dist, Lq):
+    import ctypes
+    lib = _ref_cuda()
+    wl = Workload("mid", 2, MID_LEVELS, Lq, loc_dist=dist)
+    t = make_inputs(wl, seed=17, device="cuda")
+    N, S, M, D, L, Lq, P = wl.dims()
+    vp = ctypes.c_void_p
+    ints = [ctypes.c_int] * 8
+    lib.msda_ref_fwd_f32.argtypes = [vp] * 5 + ints + [vp, vp]
+    lib.msda_ref_bwd_f32.argtypes = [vp] * 6 + ints + [vp] * 4
+    out_r = torch.empty(N, Lq, M * D, device="cuda")
+    gv_r, gl_r, ga_r = torch.empty_like(t["value"]), torch.empty_like(t["loc"]), torch.empty_like(t["aw"])
+    st = torch.cuda.current_stream().cuda_stream
+    assert lib.msda_ref_fwd_f32(t["value"].data_ptr(), t["shapes"].data_ptr(), t["lsi"].data_ptr(), t["loc"].data_ptr(),
+                                t["aw"].data_ptr(), N, S, M, D, L, Lq, P, 64, out_r.data_ptr(), st) == 0
+    assert lib.msda_ref_bwd_f32(t["grad_out"].data_ptr(), t["value"].data_ptr(), t["shapes"].data_ptr(),
+                                t["lsi"].data_ptr(), t["loc"].data_ptr(), t["aw"].data_ptr(), N, S, M, D, L, Lq, P, 64,
+                                gv_r.data_ptr(), gl_r.data_ptr(), ga_r.data_ptr(), st) == 0
+    torch.cuda.synchronize()
+    res = run_cabi("f32", *[t[k].cpu().numpy() for k in ("value", "shapes", "lsi", "loc", "aw", "grad_out")])
+    close(res["out"], out_r.cpu().numpy(), FWD_RTOL)
+    close(res["grad_value"], gv_r.cpu().numpy(), GRAD_RTOL)
+    close(res["grad_loc"], gl_r.cpu().numpy(), GRAD_RTOL)
+    close(res["grad_aw"], ga_r.cpu().numpy(), GRAD_RTOL)
+    # identical index decisions => identical touch pattern of grad_value
+    assert np.array_equal(res["grad_value"] != 0, gv_r.cpu().numpy() != 0)

@@ -1,0 +1,160 @@
+"""ctypes binding of the C ABI in include/msda_b200.h (uvhand_b200/lib/libmsda_b200.so).
+
+This is the binding a non-torch host would write (INTEGRATION.md shows it next to the reference
+call sites).  Device-pointer entry points take raw addresses (e.g. ``tensor.data_ptr()``) and a
+``cudaStream_t`` as an integer; host-buffer entry points take numpy arrays.  Nothing in here
+computes anything: a missing library is an error, never a fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_int, c_int64, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libmsda_b200.so")
+
+# every symbol include/msda_b200.h declares (tests check that the library exports exactly these)
+SYMBOLS = (
+    "msda_b200_abi_version", "msda_b200_strerror", "msda_b200_check_im2col_step",
+    "msda_fwd_f32", "msda_fwd_f64", "msda_fwd_bf16",
+    "msda_bwd_f32", "msda_bwd_f64", "msda_bwd_bf16",
+    "msda_sample_index_f32",
+    "msda_host_plan_create", "msda_host_plan_destroy", "msda_host_plan_traffic",
+    "msda_host_register", "msda_host_unregister", "msda_host_fwd_f32", "msda_host_fwd_bwd_f32",
+    "msda_b200_set_option", "msda_b200_get_option", "msda_b200_launch_count", "msda_b200_last_path",
+)
+
+_lib = None
+
+
+class MsdaError(RuntimeError):
+    def __init__(self, rc: int, what: str):
+        self.rc = rc
+        super().__init__(f"{what}: {strerror(rc)} (code {rc})")
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is not built; run `python -m uvhand_b200.build`")
+        L = ctypes.CDLL(LIB_PATH)
+        L.msda_b200_strerror.restype = c_char_p
+        L.msda_b200_strerror.argtypes = [c_int]
+        L.msda_b200_last_path.restype = c_char_p
+        L.msda_b200_last_path.argtypes = [c_int]
+        L.msda_b200_launch_count.restype = c_int64
+        L.msda_b200_set_option.argtypes = [c_char_p, c_int]
+        L.msda_b200_get_option.argtypes = [c_char_p, ctypes.POINTER(c_int)]
+        L.msda_b200_check_im2col_step.argtypes = [c_int, c_int]
+        seven = [c_int] * 7
+        for name in ("msda_fwd_f32", "msda_fwd_f64", "msda_fwd_bf16"):
+            getattr(L, name).argtypes = [c_void_p] * 5 + seven + [c_void_p, c_void_p]
+        for name in ("msda_bwd_f32", "msda_bwd_f64", "msda_bwd_bf16"):
+            getattr(L, name).argtypes = [c_void_p] * 6 + seven + [c_void_p] * 4
+        L.msda_sample_index_f32.argtypes = [c_void_p, c_void_p] + [c_int] * 5 + [c_void_p] * 4
+        L.msda_host_plan_create.argtypes = [ctypes.POINTER(c_void_p), c_int] + seven
+        L.msda_host_plan_destroy.argtypes = [c_void_p]
+        L.msda_host_plan_destroy.restype = None
+        L.msda_host_plan_traffic.argtypes = [c_void_p, ctypes.POINTER(c_int64), ctypes.POINTER(c_int64)]
+        L.msda_host_register.argtypes = [c_void_p, c_int64]
+        L.msda_host_unregister.argtypes = [c_void_p]
+        L.msda_host_fwd_f32.argtypes = [c_void_p] * 7
+        L.msda_host_fwd_bwd_f32.argtypes = [c_void_p] * 11
+        _lib = L
+    return _lib
+
+
+def strerror(rc: int) -> str:
+    return lib().msda_b200_strerror(int(rc)).decode()
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise MsdaError(rc, what)
+
+
+def set_option(key: str, value: int) -> None:
+    check(lib().msda_b200_set_option(key.encode(), int(value)), f"set_option({key})")
+
+
+def get_option(key: str) -> int:
+    v = c_int(0)
+    check(lib().msda_b200_get_option(key.encode(), ctypes.byref(v)), f"get_option({key})")
+    return v.value
+
+
+def launch_count() -> int:
+    return int(lib().msda_b200_launch_count())
+
+
+def last_path(backward: bool = False) -> str:
+    return lib().msda_b200_last_path(1 if backward else 0).decode()
+
+
+_SUFFIX = {"f32": "f32", "f64": "f64", "bf16": "bf16"}
+
+
+def forward(kind: str, value_ptr, shapes_ptr, lsi_ptr, loc_ptr, aw_ptr, dims, out_ptr, stream=0) -> None:
+    """dims = (N, S, M, D, L, Lq, P); pointers are device addresses (ints)."""
+    fn = getattr(lib(), "msda_fwd_" + _SUFFIX[kind])
+    check(fn(value_ptr, shapes_ptr, lsi_ptr, loc_ptr, aw_ptr, *dims, out_ptr, stream), "msda_fwd_" + kind)
+
+
+def backward(kind: str, go_ptr, value_ptr, shapes_ptr, lsi_ptr, loc_ptr, aw_ptr, dims,
+             gv_ptr, gl_ptr, ga_ptr, stream=0) -> None:
+    fn = getattr(lib(), "msda_bwd_" + _SUFFIX[kind])
+    check(fn(go_ptr, value_ptr, shapes_ptr, lsi_ptr, loc_ptr, aw_ptr, *dims, gv_ptr, gl_ptr, ga_ptr, stream),
+          "msda_bwd_" + kind)
+
+
+def sample_index(shapes_ptr, loc_ptr, N, Lq, M, L, P, h_ptr, w_ptr, mask_ptr, stream=0) -> None:
+    check(lib().msda_sample_index_f32(shapes_ptr, loc_ptr, N, Lq, M, L, P, h_ptr, w_ptr, mask_ptr, stream),
+          "msda_sample_index_f32")
+
+
+class HostPlan:
+    """Owns device buffers + stream for one problem size; host (numpy) arrays in and out."""
+
+    def __init__(self, N, S, M, D, L, Lq, P, device: int = 0):
+        self.dims = (N, S, M, D, L, Lq, P)
+        self._h = c_void_p()
+        check(lib().msda_host_plan_create(ctypes.byref(self._h), device, *self.dims), "msda_host_plan_create")
+
+    def close(self):
+        if self._h:
+            lib().msda_host_plan_destroy(self._h)
+            self._h = c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def traffic(self):
+        a, b = c_int64(0), c_int64(0)
+        check(lib().msda_host_plan_traffic(self._h, ctypes.byref(a), ctypes.byref(b)), "msda_host_plan_traffic")
+        return a.value, b.value
+
+    @staticmethod
+    def _p(a):
+        return a.ctypes.data_as(c_void_p)
+
+    def forward(self, value, shapes, lsi, loc, aw, out):
+        check(lib().msda_host_fwd_f32(self._h, self._p(value), self._p(shapes), self._p(lsi), self._p(loc),
+                                      self._p(aw), self._p(out)), "msda_host_fwd_f32")
+
+    def forward_backward(self, value, shapes, lsi, loc, aw, grad_out, out, gv, gl, ga):
+        check(lib().msda_host_fwd_bwd_f32(self._h, self._p(value), self._p(shapes), self._p(lsi), self._p(loc),
+                                          self._p(aw), self._p(grad_out), self._p(out), self._p(gv),
+                                          self._p(gl), self._p(ga)), "msda_host_fwd_bwd_f32")
+
+
+def host_register(arr) -> None:
+    check(lib().msda_host_register(arr.ctypes.data_as(c_void_p), arr.nbytes), "msda_host_register")
+
+
+def host_unregister(arr) -> None:
+    check(lib().msda_host_unregister(arr.ctypes.data_as(c_void_p)), "msda_host_unregister")

@@ -1,0 +1,484 @@
+// C ABI of the B200-native MSDeformAttn operator (declared in include/msda_b200.h).
+// Torch-free: plain pointers, sizes and a cudaStream_t.  Compiled for sm_100a only.
+//
+// Replaces, in the reference tree (/root/reference/models/ops/src):
+//   cuda/ms_deform_im2col_cuda.cuh:923-954   ms_deformable_im2col_cuda<T>   -> msda_fwd_*
+//   cuda/ms_deform_im2col_cuda.cuh:956-1327  ms_deformable_col2im_cuda<T>   -> msda_bwd_*
+//   cuda/ms_deform_attn_cuda.cu:50-52        chunking precondition          -> msda_b200_check_im2col_step
+#include "../../include/msda_b200.h"
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "msda_d32.cuh"
+#include "msda_generic.cuh"
+
+namespace {
+
+using namespace msda;
+
+std::atomic<int> g_fwd_path{0};
+std::atomic<int> g_bwd_path{0};
+std::atomic<long long> g_launches{0};
+const char* g_last_path[2] = {"none", "none"};
+
+int sm_count() {
+  static int cached = 0;
+  if (cached == 0) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) {
+      cudaGetLastError();
+      return 148;
+    }
+    cached = n;
+  }
+  return cached;
+}
+
+bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
+
+int check_dims(int N, int S, int M, int D, int L, int Lq, int P) {
+  if (N < 0 || S < 0 || M < 0 || D < 0 || L < 0 || Lq < 0 || P < 0) return MSDA_ERR_BAD_DIMS;
+  // Flat element counts must fit in int64 comfortably; each factor is < 2^31 so two-by-two
+  // products are safe, and we bound the totals at 2^46 elements (far beyond 180 GB).
+  const long double lim = 70368744177664.0L;
+  if ((long double)N * S * M * D > lim) return MSDA_ERR_BAD_DIMS;
+  if ((long double)N * Lq * M * L * P * 2 > lim) return MSDA_ERR_BAD_DIMS;
+  if ((long double)N * Lq * M * D > lim) return MSDA_ERR_BAD_DIMS;
+  return MSDA_OK;
+}
+
+bool nothing_to_do(int N, int M, int D, int Lq) { return N == 0 || M == 0 || D == 0 || Lq == 0; }
+
+int finish_launch(int n_launched) {
+  g_launches.fetch_add(n_launched, std::memory_order_relaxed);
+  const cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? MSDA_OK : (int)e;
+}
+
+// The specialised kernels address value rows with 32-bit chunk offsets inside one sample.
+bool d32_eligible(int S, int M, int D, int L, int P) {
+  return D == 32 && L >= 1 && L <= kMaxLevelsD32 && L * P >= 1 && L * P <= kMaxLPD32 &&
+         (long long)S * M * 8 < (1ll << 31);
+}
+
+int d32_grid(long long n_items) {
+  const long long n_pass = (n_items + kItemsPerWarp - 1) / kItemsPerWarp;
+  long long ctas = (n_pass + kD32Warps - 1) / kD32Warps;
+  const long long cap = (long long)sm_count() * 64;
+  if (ctas > cap) ctas = cap;
+  if (ctas < 1) ctas = 1;
+  return (int)ctas;
+}
+
+size_t d32_smem(int LP) { return (size_t)kD32Warps * 2 * kItemsPerWarp * LP * 16; }
+
+int generic_grid(long long n_items) {
+  long long ctas = (n_items + (kGenericThreads / kWarp) - 1) / (kGenericThreads / kWarp);
+  const long long cap = (long long)sm_count() * 64;
+  if (ctas > cap) ctas = cap;
+  if (ctas < 1) ctas = 1;
+  return (int)ctas;
+}
+
+template <typename VT>
+int launch_fwd_d32(const D32Params& p, cudaStream_t st) {
+  const int LP = p.L * p.P;
+  const int grid = d32_grid(p.n_items);
+  if (LP == 16) {
+    fwd_d32_kernel<VT, 16><<<grid, kD32Threads, d32_smem(LP), st>>>(p);
+  } else {
+    fwd_d32_kernel<VT, 0><<<grid, kD32Threads, d32_smem(LP), st>>>(p);
+  }
+  return finish_launch(1);
+}
+
+template <typename VT>
+int launch_bwd_d32(const D32Params& p, cudaStream_t st) {
+  const int LP = p.L * p.P;
+  const int grid = d32_grid(p.n_items);
+  if (LP == 16) {
+    bwd_d32_kernel<VT, 16><<<grid, kD32Threads, d32_smem(LP), st>>>(p);
+  } else {
+    bwd_d32_kernel<VT, 0><<<grid, kD32Threads, d32_smem(LP), st>>>(p);
+  }
+  return finish_launch(1);
+}
+
+template <typename T>
+int fwd_any(const T* value, const int64_t* shapes, const int64_t* lsi, const T* loc, const T* aw,
+            int N, int S, int M, int D, int L, int Lq, int P, T* out, cudaStream_t st) {
+  const Dims d{N, S, M, D, L, Lq, P};
+  const long long n_items = (long long)N * Lq * M;
+  fwd_generic_kernel<T><<<generic_grid(n_items), kGenericThreads, 0, st>>>(value, shapes, lsi, loc, aw, d, out);
+  return finish_launch(1);
+}
+
+template <typename T>
+int bwd_any(const T* go, const T* value, const int64_t* shapes, const int64_t* lsi, const T* loc,
+            const T* aw, int N, int S, int M, int D, int L, int Lq, int P, T* gv, T* gl, T* ga,
+            cudaStream_t st) {
+  const Dims d{N, S, M, D, L, Lq, P};
+  const long long n_items = (long long)N * Lq * M;
+  bwd_generic_kernel<T><<<generic_grid(n_items), kGenericThreads, 0, st>>>(go, value, shapes, lsi, loc, aw, d, gv, gl, ga);
+  return finish_launch(1);
+}
+
+}  // namespace
+
+extern "C" {
+
+int msda_b200_abi_version(void) { return MSDA_B200_ABI_VERSION; }
+
+const char* msda_b200_strerror(int rc) {
+  switch (rc) {
+    case MSDA_OK: return "ok";
+    case MSDA_ERR_NULL_POINTER: return "msda: required pointer is NULL";
+    case MSDA_ERR_BAD_DIMS: return "msda: negative dimension or size overflow";
+    case MSDA_ERR_IM2COL_STEP: return "msda: batch must be divisible by min(batch, im2col_step)";
+    case MSDA_ERR_UNSUPPORTED: return "msda: unsupported combination (bf16 value needs channels == 32, levels <= 8, levels*points <= 32)";
+    case MSDA_ERR_MISALIGNED: return "msda: pointer not aligned to its element size";
+    case MSDA_ERR_NO_DEVICE: return "msda: no usable CUDA device";
+    case MSDA_ERR_BAD_OPTION: return "msda: unknown option key or value";
+    default: break;
+  }
+  if (rc > 0) return cudaGetErrorString((cudaError_t)rc);
+  return "msda: unknown error";
+}
+
+int msda_b200_check_im2col_step(int batch, int im2col_step) {
+  const int step = batch < im2col_step ? batch : im2col_step;
+  if (batch == 0) return MSDA_OK;
+  if (step <= 0 || batch % step != 0) return MSDA_ERR_IM2COL_STEP;
+  return MSDA_OK;
+}
+
+int msda_b200_set_option(const char* key, int value) {
+  if (!key) return MSDA_ERR_BAD_OPTION;
+  if (!strcmp(key, "fwd_path")) {
+    if (value < 0 || value > 2) return MSDA_ERR_BAD_OPTION;
+    g_fwd_path.store(value);
+    return MSDA_OK;
+  }
+  if (!strcmp(key, "bwd_path")) {
+    if (value < 0 || value > 2) return MSDA_ERR_BAD_OPTION;
+    g_bwd_path.store(value);
+    return MSDA_OK;
+  }
+  return MSDA_ERR_BAD_OPTION;
+}
+
+int msda_b200_get_option(const char* key, int* value) {
+  if (!key || !value) return MSDA_ERR_BAD_OPTION;
+  if (!strcmp(key, "fwd_path")) { *value = g_fwd_path.load(); return MSDA_OK; }
+  if (!strcmp(key, "bwd_path")) { *value = g_bwd_path.load(); return MSDA_OK; }
+  return MSDA_ERR_BAD_OPTION;
+}
+
+int64_t msda_b200_launch_count(void) { return (int64_t)g_launches.load(); }
+
+const char* msda_b200_last_path(int backward) { return g_last_path[backward ? 1 : 0]; }
+
+// ---- forward ------------------------------------------------------------------------------
+
+int msda_fwd_f32(const float* value, const int64_t* shapes, const int64_t* lsi, const float* loc,
+                 const float* aw, int N, int S, int M, int D, int L, int Lq, int P, float* out,
+                 void* stream) {
+  int rc = check_dims(N, S, M, D, L, Lq, P);
+  if (rc) return rc;
+  if (nothing_to_do(N, M, D, Lq)) return MSDA_OK;
+  if (!out) return MSDA_ERR_NULL_POINTER;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (L == 0 || P == 0 || S == 0) {  // no samples: the sum is empty
+    const cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float) * (size_t)N * Lq * M * D, st);
+    return e == cudaSuccess ? MSDA_OK : (int)e;
+  }
+  if (!value || !shapes || !lsi || !loc || !aw) return MSDA_ERR_NULL_POINTER;
+  if (!aligned(value, 4) || !aligned(loc, 4) || !aligned(aw, 4) || !aligned(out, 4) ||
+      !aligned(shapes, 8) || !aligned(lsi, 8))
+    return MSDA_ERR_MISALIGNED;
+  const int path = g_fwd_path.load();
+  const bool fast = path != 1 && d32_eligible(S, M, D, L, P) && aligned(value, 16) &&
+                    aligned(out, 16) && aligned(loc, 8);
+  if (fast) {
+    D32Params p{};
+    p.value = value; p.shapes = shapes; p.lsi = lsi; p.loc = loc; p.aw = aw; p.out = out;
+    p.N = N; p.S = S; p.M = M; p.L = L; p.Lq = Lq; p.P = P;
+    p.n_items = (long long)N * Lq * M;
+    g_last_path[0] = "fwd_d32_f32";
+    return launch_fwd_d32<float>(p, st);
+  }
+  g_last_path[0] = "fwd_generic_f32";
+  return fwd_any<float>(value, shapes, lsi, loc, aw, N, S, M, D, L, Lq, P, out, st);
+}
+
+int msda_fwd_f64(const double* value, const int64_t* shapes, const int64_t* lsi, const double* loc,
+                 const double* aw, int N, int S, int M, int D, int L, int Lq, int P, double* out,
+                 void* stream) {
+  int rc = check_dims(N, S, M, D, L, Lq, P);
+  if (rc) return rc;
+  if (nothing_to_do(N, M, D, Lq)) return MSDA_OK;
+  if (!out) return MSDA_ERR_NULL_POINTER;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (L == 0 || P == 0 || S == 0) {
+    const cudaError_t e = cudaMemsetAsync(out, 0, sizeof(double) * (size_t)N * Lq * M * D, st);
+    return e == cudaSuccess ? MSDA_OK : (int)e;
+  }
+  if (!value || !shapes || !lsi || !loc || !aw) return MSDA_ERR_NULL_POINTER;
+  if (!aligned(value, 8) || !aligned(loc, 8) || !aligned(aw, 8) || !aligned(out, 8) ||
+      !aligned(shapes, 8) || !aligned(lsi, 8))
+    return MSDA_ERR_MISALIGNED;
+  g_last_path[0] = "fwd_generic_f64";
+  return fwd_any<double>(value, shapes, lsi, loc, aw, N, S, M, D, L, Lq, P, out, st);
+}
+
+int msda_fwd_bf16(const uint16_t* value, const int64_t* shapes, const int64_t* lsi, const float* loc,
+                  const float* aw, int N, int S, int M, int D, int L, int Lq, int P, float* out,
+                  void* stream) {
+  int rc = check_dims(N, S, M, D, L, Lq, P);
+  if (rc) return rc;
+  if (nothing_to_do(N, M, D, Lq)) return MSDA_OK;
+  if (!out) return MSDA_ERR_NULL_POINTER;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (L == 0 || P == 0 || S == 0) {
+    const cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float) * (size_t)N * Lq * M * D, st);
+    return e == cudaSuccess ? MSDA_OK : (int)e;
+  }
+  if (!value || !shapes || !lsi || !loc || !aw) return MSDA_ERR_NULL_POINTER;
+  if (!d32_eligible(S, M, D, L, P)) return MSDA_ERR_UNSUPPORTED;
+  if (!aligned(value, 8) || !aligned(out, 16) || !aligned(loc, 8) || !aligned(aw, 4) ||
+      !aligned(shapes, 8) || !aligned(lsi, 8))
+    return MSDA_ERR_MISALIGNED;
+  D32Params p{};
+  p.value = value; p.shapes = shapes; p.lsi = lsi; p.loc = loc; p.aw = aw; p.out = out;
+  p.N = N; p.S = S; p.M = M; p.L = L; p.Lq = Lq; p.P = P;
+  p.n_items = (long long)N * Lq * M;
+  g_last_path[0] = "fwd_d32_bf16";
+  return launch_fwd_d32<__nv_bfloat16>(p, st);
+}
+
+// ---- backward -----------------------------------------------------------------------------
+
+int msda_bwd_f32(const float* go, const float* value, const int64_t* shapes, const int64_t* lsi,
+                 const float* loc, const float* aw, int N, int S, int M, int D, int L, int Lq, int P,
+                 float* gv, float* gl, float* ga, void* stream) {
+  int rc = check_dims(N, S, M, D, L, Lq, P);
+  if (rc) return rc;
+  if (nothing_to_do(N, M, D, Lq) || L == 0 || P == 0 || S == 0) return MSDA_OK;
+  if (!go || !value || !shapes || !lsi || !loc || !aw || !gv || !gl || !ga) return MSDA_ERR_NULL_POINTER;
+  if (!aligned(go, 4) || !aligned(value, 4) || !aligned(loc, 4) || !aligned(aw, 4) || !aligned(gv, 4) ||
+      !aligned(gl, 4) || !aligned(ga, 4) || !aligned(shapes, 8) || !aligned(lsi, 8))
+    return MSDA_ERR_MISALIGNED;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int path = g_bwd_path.load();
+  const bool fast = path != 1 && d32_eligible(S, M, D, L, P) && aligned(value, 16) && aligned(gv, 16) &&
+                    aligned(go, 16) && aligned(loc, 8) && aligned(gl, 8);
+  if (fast) {
+    D32Params p{};
+    p.value = value; p.shapes = shapes; p.lsi = lsi; p.loc = loc; p.aw = aw; p.grad_out = go;
+    p.grad_value = gv; p.grad_loc = gl; p.grad_aw = ga;
+    p.N = N; p.S = S; p.M = M; p.L = L; p.Lq = Lq; p.P = P;
+    p.n_items = (long long)N * Lq * M;
+    g_last_path[1] = "bwd_d32_f32";
+    return launch_bwd_d32<float>(p, st);
+  }
+  g_last_path[1] = "bwd_generic_f32";
+  return bwd_any<float>(go, value, shapes, lsi, loc, aw, N, S, M, D, L, Lq, P, gv, gl, ga, st);
+}
+
+int msda_bwd_f64(const double* go, const double* value, const int64_t* shapes, const int64_t* lsi,
+                 const double* loc, const double* aw, int N, int S, int M, int D, int L, int Lq, int P,
+                 double* gv, double* gl, double* ga, void* stream) {
+  int rc = check_dims(N, S, M, D, L, Lq, P);
+  if (rc) return rc;
+  if (nothing_to_do(N, M, D, Lq) || L == 0 || P == 0 || S == 0) return MSDA_OK;
+  if (!go || !value || !shapes || !lsi || !loc || !aw || !gv || !gl || !ga) return MSDA_ERR_NULL_POINTER;
+  if (!aligned(go, 8) || !aligned(value, 8) || !aligned(loc, 8) || !aligned(aw, 8) || !aligned(gv, 8) ||
+      !aligned(gl, 8) || !aligned(ga, 8) || !aligned(shapes, 8) || !aligned(lsi, 8))
+    return MSDA_ERR_MISALIGNED;
+  g_last_path[1] = "bwd_generic_f64";
+  return bwd_any<double>(go, value, shapes, lsi, loc, aw, N, S, M, D, L, Lq, P, gv, gl, ga,
+                         (cudaStream_t)stream);
+}
+
+int msda_bwd_bf16(const float* go, const uint16_t* value, const int64_t* shapes, const int64_t* lsi,
+                  const float* loc, const float* aw, int N, int S, int M, int D, int L, int Lq, int P,
+                  uint16_t* gv, float* gl, float* ga, void* stream) {
+  int rc = check_dims(N, S, M, D, L, Lq, P);
+  if (rc) return rc;
+  if (nothing_to_do(N, M, D, Lq) || L == 0 || P == 0 || S == 0) return MSDA_OK;
+  if (!go || !value || !shapes || !lsi || !loc || !aw || !gv || !gl || !ga) return MSDA_ERR_NULL_POINTER;
+  if (!d32_eligible(S, M, D, L, P)) return MSDA_ERR_UNSUPPORTED;
+  if (!aligned(go, 16) || !aligned(value, 8) || !aligned(gv, 8) || !aligned(loc, 8) || !aligned(aw, 4) ||
+      !aligned(gl, 8) || !aligned(ga, 4) || !aligned(shapes, 8) || !aligned(lsi, 8))
+    return MSDA_ERR_MISALIGNED;
+  D32Params p{};
+  p.value = value; p.shapes = shapes; p.lsi = lsi; p.loc = loc; p.aw = aw; p.grad_out = go;
+  p.grad_value = gv; p.grad_loc = gl; p.grad_aw = ga;
+  p.N = N; p.S = S; p.M = M; p.L = L; p.Lq = Lq; p.P = P;
+  p.n_items = (long long)N * Lq * M;
+  g_last_path[1] = "bwd_d32_bf16";
+  return launch_bwd_d32<__nv_bfloat16>(p, (cudaStream_t)stream);
+}
+
+// ---- parity probe -------------------------------------------------------------------------
+
+int msda_sample_index_f32(const int64_t* shapes, const float* loc, int N, int Lq, int M, int L, int P,
+                          int32_t* h_low, int32_t* w_low, uint8_t* mask, void* stream) {
+  if (N < 0 || Lq < 0 || M < 0 || L < 0 || P < 0) return MSDA_ERR_BAD_DIMS;
+  const long long n = (long long)N * Lq * M * L * P;
+  if (n == 0) return MSDA_OK;
+  if (!shapes || !loc || !h_low || !w_low || !mask) return MSDA_ERR_NULL_POINTER;
+  long long blocks = (n + 255) / 256;
+  const long long cap = (long long)sm_count() * 32;
+  if (blocks > cap) blocks = cap;
+  sample_index_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(shapes, loc, n, L, P, h_low, w_low, mask);
+  return finish_launch(1);
+}
+
+// ---- host-buffer entry points -------------------------------------------------------------
+
+struct msda_host_plan {
+  int device;
+  int N, S, M, D, L, Lq, P;
+  size_t n_value, n_loc, n_aw, n_out;
+  float *d_value, *d_loc, *d_aw, *d_go, *d_out, *d_gv, *d_gl, *d_ga;
+  int64_t *d_shapes, *d_lsi;
+  cudaStream_t stream;
+};
+
+#define MSDA_CUDA_TRY(expr)                     \
+  do {                                          \
+    const cudaError_t e__ = (expr);             \
+    if (e__ != cudaSuccess) return (int)e__;    \
+  } while (0)
+
+int msda_host_plan_create(msda_host_plan** out_plan, int device, int N, int S, int M, int D, int L,
+                          int Lq, int P) {
+  if (!out_plan) return MSDA_ERR_NULL_POINTER;
+  *out_plan = nullptr;
+  int rc = check_dims(N, S, M, D, L, Lq, P);
+  if (rc) return rc;
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || device < 0 || device >= n_dev) {
+    cudaGetLastError();
+    return MSDA_ERR_NO_DEVICE;
+  }
+  MSDA_CUDA_TRY(cudaSetDevice(device));
+  msda_host_plan* pl = new (std::nothrow) msda_host_plan();
+  if (!pl) return (int)cudaErrorMemoryAllocation;
+  memset(pl, 0, sizeof(*pl));
+  pl->device = device;
+  pl->N = N; pl->S = S; pl->M = M; pl->D = D; pl->L = L; pl->Lq = Lq; pl->P = P;
+  pl->n_value = (size_t)N * S * M * D;
+  pl->n_aw = (size_t)N * Lq * M * L * P;
+  pl->n_loc = pl->n_aw * 2;
+  pl->n_out = (size_t)N * Lq * M * D;
+  cudaError_t e = cudaStreamCreateWithFlags(&pl->stream, cudaStreamNonBlocking);
+  auto alloc = [&](float** p, size_t n) {
+    if (e == cudaSuccess) e = cudaMalloc((void**)p, sizeof(float) * (n ? n : 1));
+  };
+  alloc(&pl->d_value, pl->n_value);
+  alloc(&pl->d_loc, pl->n_loc);
+  alloc(&pl->d_aw, pl->n_aw);
+  alloc(&pl->d_go, pl->n_out);
+  alloc(&pl->d_out, pl->n_out);
+  alloc(&pl->d_gv, pl->n_value);
+  alloc(&pl->d_gl, pl->n_loc);
+  alloc(&pl->d_ga, pl->n_aw);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&pl->d_shapes, sizeof(int64_t) * 2 * (L ? L : 1));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&pl->d_lsi, sizeof(int64_t) * (L ? L : 1));
+  if (e != cudaSuccess) {
+    msda_host_plan_destroy(pl);
+    return (int)e;
+  }
+  *out_plan = pl;
+  return MSDA_OK;
+}
+
+void msda_host_plan_destroy(msda_host_plan* pl) {
+  if (!pl) return;
+  cudaSetDevice(pl->device);
+  cudaFree(pl->d_value); cudaFree(pl->d_loc); cudaFree(pl->d_aw); cudaFree(pl->d_go);
+  cudaFree(pl->d_out); cudaFree(pl->d_gv); cudaFree(pl->d_gl); cudaFree(pl->d_ga);
+  cudaFree(pl->d_shapes); cudaFree(pl->d_lsi);
+  if (pl->stream) cudaStreamDestroy(pl->stream);
+  delete pl;
+}
+
+int msda_host_plan_traffic(const msda_host_plan* pl, int64_t* h2d, int64_t* d2h) {
+  if (!pl) return MSDA_ERR_NULL_POINTER;
+  const int64_t in = (int64_t)sizeof(float) * (pl->n_value + pl->n_loc + pl->n_aw + pl->n_out) +
+                     (int64_t)sizeof(int64_t) * 3 * pl->L;
+  const int64_t out = (int64_t)sizeof(float) * (pl->n_out + pl->n_value + pl->n_loc + pl->n_aw);
+  if (h2d) *h2d = in;
+  if (d2h) *d2h = out;
+  return MSDA_OK;
+}
+
+int msda_host_register(void* ptr, int64_t bytes) {
+  if (!ptr || bytes <= 0) return MSDA_ERR_NULL_POINTER;
+  MSDA_CUDA_TRY(cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterDefault));
+  return MSDA_OK;
+}
+
+int msda_host_unregister(void* ptr) {
+  if (!ptr) return MSDA_ERR_NULL_POINTER;
+  MSDA_CUDA_TRY(cudaHostUnregister(ptr));
+  return MSDA_OK;
+}
+
+static int host_upload(msda_host_plan* pl, const float* value, const int64_t* shapes,
+                       const int64_t* lsi, const float* loc, const float* aw) {
+  cudaStream_t st = pl->stream;
+  MSDA_CUDA_TRY(cudaMemcpyAsync(pl->d_shapes, shapes, sizeof(int64_t) * 2 * pl->L, cudaMemcpyHostToDevice, st));
+  MSDA_CUDA_TRY(cudaMemcpyAsync(pl->d_lsi, lsi, sizeof(int64_t) * pl->L, cudaMemcpyHostToDevice, st));
+  MSDA_CUDA_TRY(cudaMemcpyAsync(pl->d_value, value, sizeof(float) * pl->n_value, cudaMemcpyHostToDevice, st));
+  MSDA_CUDA_TRY(cudaMemcpyAsync(pl->d_loc, loc, sizeof(float) * pl->n_loc, cudaMemcpyHostToDevice, st));
+  MSDA_CUDA_TRY(cudaMemcpyAsync(pl->d_aw, aw, sizeof(float) * pl->n_aw, cudaMemcpyHostToDevice, st));
+  return MSDA_OK;
+}
+
+int msda_host_fwd_f32(msda_host_plan* pl, const float* value, const int64_t* shapes, const int64_t* lsi,
+                      const float* loc, const float* aw, float* out) {
+  if (!pl || !value || !shapes || !lsi || !loc || !aw || !out) return MSDA_ERR_NULL_POINTER;
+  MSDA_CUDA_TRY(cudaSetDevice(pl->device));
+  int rc = host_upload(pl, value, shapes, lsi, loc, aw);
+  if (rc) return rc;
+  rc = msda_fwd_f32(pl->d_value, pl->d_shapes, pl->d_lsi, pl->d_loc, pl->d_aw, pl->N, pl->S, pl->M,
+                    pl->D, pl->L, pl->Lq, pl->P, pl->d_out, pl->stream);
+  if (rc) return rc;
+  MSDA_CUDA_TRY(cudaMemcpyAsync(out, pl->d_out, sizeof(float) * pl->n_out, cudaMemcpyDeviceToHost, pl->stream));
+  MSDA_CUDA_TRY(cudaStreamSynchronize(pl->stream));
+  return MSDA_OK;
+}
+
+int msda_host_fwd_bwd_f32(msda_host_plan* pl, const float* value, const int64_t* shapes,
+                          const int64_t* lsi, const float* loc, const float* aw, const float* go,
+                          float* out, float* gv, float* gl, float* ga) {
+  if (!pl || !value || !shapes || !lsi || !loc || !aw || !go || !out || !gv || !gl || !ga)
+    return MSDA_ERR_NULL_POINTER;
+  MSDA_CUDA_TRY(cudaSetDevice(pl->device));
+  cudaStream_t st = pl->stream;
+  int rc = host_upload(pl, value, shapes, lsi, loc, aw);
+  if (rc) return rc;
+  rc = msda_fwd_f32(pl->d_value, pl->d_shapes, pl->d_lsi, pl->d_loc, pl->d_aw, pl->N, pl->S, pl->M,
+                    pl->D, pl->L, pl->Lq, pl->P, pl->d_out, st);
+  if (rc) return rc;
+  MSDA_CUDA_TRY(cudaMemcpyAsync(out, pl->d_out, sizeof(float) * pl->n_out, cudaMemcpyDeviceToHost, st));
+  MSDA_CUDA_TRY(cudaMemcpyAsync(pl->d_go, go, sizeof(float) * pl->n_out, cudaMemcpyHostToDevice, st));
+  MSDA_CUDA_TRY(cudaMemsetAsync(pl->d_gv, 0, sizeof(float) * pl->n_value, st));
+  rc = msda_bwd_f32(pl->d_go, pl->d_value, pl->d_shapes, pl->d_lsi, pl->d_loc, pl->d_aw, pl->N, pl->S,
+                    pl->M, pl->D, pl->L, pl->Lq, pl->P, pl->d_gv, pl->d_gl, pl->d_ga, st);
+  if (rc) return rc;
+  MSDA_CUDA_TRY(cudaMemcpyAsync(gv, pl->d_gv, sizeof(float) * pl->n_value, cudaMemcpyDeviceToHost, st));
+  MSDA_CUDA_TRY(cudaMemcpyAsync(gl, pl->d_gl, sizeof(float) * pl->n_loc, cudaMemcpyDeviceToHost, st));
+  MSDA_CUDA_TRY(cudaMemcpyAsync(ga, pl->d_ga, sizeof(float) * pl->n_aw, cudaMemcpyDeviceToHost, st));
+  MSDA_CUDA_TRY(cudaStreamSynchronize(st));
+  return MSDA_OK;
+}
+
+}  // extern "C"

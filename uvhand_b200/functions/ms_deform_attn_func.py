@@ -1,0 +1,76 @@
+"""Autograd boundary of the operator -- same class name, same ``apply`` signature and the same
+returned gradients as the reference's
+/root/reference/models/ops/functions/ms_deform_attn_func.py:21-39, so every model of the
+reference tree (H2OTR/ARCTIC, AssemblyHands, DINO, DN-DAB) picks the sm_100a kernels up unchanged.
+
+    MSDeformAttnFunction.apply(value, value_spatial_shapes, value_level_start_index,
+                               sampling_locations, attention_weights, im2col_step)
+
+dtype policy at this boundary ("dtype policy"):
+  * float32 value                     -> fp32 kernels (all three reference copies end up here);
+  * float64 value with float64 loc/w  -> fp64 kernels (what models/dino/ops allows; the reference's
+                                         own test.py fp64 checks need it);
+  * bfloat16 value, float32 loc/w     -> native bf16-value kernels ONLY when the opt-in switch is
+                                         on (``set_bf16_value_mode(True)`` or MSDA_B200_BF16_VALUE=1);
+  * anything else                     -> ``value.to(float32)``, which is what models/ops does for
+                                         every input (func.py:26,37).
+There is no fallback implementation here: the extension must be present.
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from .. import load_extension
+
+MSDA = load_extension()
+
+_bf16_value_mode = os.environ.get("MSDA_B200_BF16_VALUE", "0") not in ("", "0", "false", "False")
+
+
+def set_bf16_value_mode(enabled: bool) -> None:
+    """Opt in/out of handing bfloat16 ``value`` tensors to the kernels as they are (half the
+    gather bytes; grad_value is then accumulated in bfloat16).  Off by default = reference numerics."""
+    global _bf16_value_mode
+    _bf16_value_mode = bool(enabled)
+
+
+def get_bf16_value_mode() -> bool:
+    return _bf16_value_mode
+
+
+def _kernel_value(value: torch.Tensor, sampling_locations: torch.Tensor) -> torch.Tensor:
+    if value.dtype == torch.float32:
+        return value
+    if value.dtype == torch.float64 and sampling_locations.dtype == torch.float64:
+        return value
+    if value.dtype == torch.bfloat16 and _bf16_value_mode and sampling_locations.dtype == torch.float32:
+        return value
+    return value.to(torch.float32)
+
+
+class MSDeformAttnFunction(Function):
+    @staticmethod
+    def forward(ctx, value, value_spatial_shapes, value_level_start_index, sampling_locations,
+                attention_weights, im2col_step):
+        ctx.im2col_step = im2col_step
+        output = MSDA.ms_deform_attn_forward(
+            _kernel_value(value, sampling_locations), value_spatial_shapes, value_level_start_index,
+            sampling_locations, attention_weights, ctx.im2col_step)
+        # like the reference, the tensor as given (not the cast copy) is what is kept alive
+        ctx.save_for_backward(value, value_spatial_shapes, value_level_start_index,
+                              sampling_locations, attention_weights)
+        return output
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        value, value_spatial_shapes, value_level_start_index, sampling_locations, attention_weights = \
+            ctx.saved_tensors
+        grad_value, grad_sampling_loc, grad_attn_weight = MSDA.ms_deform_attn_backward(
+            _kernel_value(value, sampling_locations), value_spatial_shapes, value_level_start_index,
+            sampling_locations, attention_weights, grad_output.contiguous(), ctx.im2col_step)
+        return grad_value, None, None, grad_sampling_loc, grad_attn_weight, None

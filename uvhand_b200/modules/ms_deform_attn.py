@@ -1,0 +1,121 @@
+"""``MSDeformAttn`` -- the nn.Module that produces the operator's inputs and consumes its output.
+
+Drop-in for /root/reference/models/ops/modules/ms_deform_attn.py:30-140 (and its two sibling
+copies): same constructor, same four ``nn.Linear`` children with the same
+names (``sampling_offsets``, ``attention_weights``, ``value_proj``, ``output_proj``) so reference
+checkpoints load unchanged, same initialisation, same forward contract.  The hot op goes through
+``MSDeformAttnFunction`` (sm_100a kernels); everything else here is plain torch plumbing around it.
+
+Reference-point forms accepted (last dim of ``reference_points``):
+  2   (x, y) per level                           -- ms_deform_attn.py:105-108
+  42  21 hand keypoints (x0,y0,...,x20,y20); their mean is the sampling centre -- :110-128 (UVHand)
+  4   (cx, cy, w, h) boxes                       -- models/dn_dab_dino_deformable_detr/ops/modules/ms_deform_attn.py:106-108
+"""
+from __future__ import annotations
+
+import math
+import warnings
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from ..functions.ms_deform_attn_func import MSDeformAttnFunction
+
+
+def _power_of_two(n) -> bool:
+    if not isinstance(n, int) or n < 0:
+        raise ValueError(f"invalid input for _is_power_of_2: {n} (type: {type(n)})")
+    return n != 0 and (n & (n - 1)) == 0
+
+
+class MSDeformAttn(nn.Module):
+    def __init__(self, d_model: int = 256, n_levels: int = 4, n_heads: int = 8, n_points: int = 4):
+        super().__init__()
+        if d_model % n_heads != 0:
+            raise ValueError(f"d_model must be divisible by n_heads, but got {d_model} and {n_heads}")
+        if not _power_of_two(d_model // n_heads):
+            warnings.warn("MSDeformAttn: channels per head is not a power of two; the sm_100a fast "
+                          "path is specialised for 32 channels per head, other sizes use the "
+                          "any-shape kernels.")
+        self.im2col_step = 64          # kept for interface parity (ms_deform_attn.py:48)
+        self.d_model = d_model
+        self.n_levels = n_levels
+        self.n_heads = n_heads
+        self.n_points = n_points
+
+        self.sampling_offsets = nn.Linear(d_model, n_heads * n_levels * n_points * 2)
+        self.attention_weights = nn.Linear(d_model, n_heads * n_levels * n_points)
+        self.value_proj = nn.Linear(d_model, d_model)
+        self.output_proj = nn.Linear(d_model, d_model)
+        self._reset_parameters()
+
+    def _reset_parameters(self):
+        # Offsets start as a ring: head h looks along angle 2*pi*h/M, point i sits i+1 pixels out
+        # (ms_deform_attn.py:62-70); attention starts uniform (:73-74).
+        nn.init.constant_(self.sampling_offsets.weight, 0.0)
+        angle = torch.arange(self.n_heads, dtype=torch.float32) * (2.0 * math.pi / self.n_heads)
+        ring = torch.stack([angle.cos(), angle.sin()], dim=-1)
+        ring = ring / ring.abs().max(dim=-1, keepdim=True)[0]
+        ring = ring.view(self.n_heads, 1, 1, 2).repeat(1, self.n_levels, self.n_points, 1)
+        ring = ring * torch.arange(1, self.n_points + 1, dtype=torch.float32).view(1, 1, -1, 1)
+        with torch.no_grad():
+            self.sampling_offsets.bias = nn.Parameter(ring.reshape(-1))
+        nn.init.constant_(self.attention_weights.weight, 0.0)
+        nn.init.constant_(self.attention_weights.bias, 0.0)
+        nn.init.xavier_uniform_(self.value_proj.weight)
+        nn.init.constant_(self.value_proj.bias, 0.0)
+        nn.init.xavier_uniform_(self.output_proj.weight)
+        nn.init.constant_(self.output_proj.bias, 0.0)
+
+    @staticmethod
+    def _sampling_locations(reference_points, offsets, spatial_shapes):
+        """reference_points [N, Lq, L, C], offsets [N, Lq, M, L, P, 2] -> locations, same shape as offsets."""
+        # (W_l, H_l): offsets are in pixels of their own level
+        wh = torch.stack([spatial_shapes[..., 1], spatial_shapes[..., 0]], dim=-1)
+        wh = wh[None, None, None, :, None, :]
+        c = reference_points.shape[-1]
+        if c == 2:
+            return reference_points[:, :, None, :, None, :] + offsets / wh
+        if c == 42:
+            # centre of the 21 keypoints (the "center refine" variant the reference ships)
+            kp = reference_points[:, :, None, :, None, :]
+            centre = torch.stack([kp[..., 0::2].mean(-1), kp[..., 1::2].mean(-1)], dim=-1)
+            return centre + offsets / wh
+        if c == 4:
+            n_points = offsets.shape[4]
+            box = reference_points[:, :, None, :, None, :]
+            return box[..., :2] + offsets / n_points * box[..., 2:] * 0.5
+        raise ValueError(f"Last dim of reference_points must be 2, 4 or 42, but get {c} instead.")
+
+    def forward(self, query, reference_points, input_flatten, input_spatial_shapes,
+                input_level_start_index, input_padding_mask=None):
+        """query [N, Lq, C]; reference_points [N, Lq, L, 2|4|42] in [0,1] image coordinates;
+        input_flatten [N, S, C] with S = sum_l H_l*W_l; input_spatial_shapes [L, 2] = (H_l, W_l);
+        input_level_start_index [L]; input_padding_mask [N, S] (True = padding).  -> [N, Lq, C]"""
+        n, len_q, _ = query.shape
+        n, len_in, _ = input_flatten.shape
+        assert (input_spatial_shapes[:, 0] * input_spatial_shapes[:, 1]).sum() == len_in
+
+        value = self.value_proj(input_flatten)
+        if input_padding_mask is not None:
+            value = value.masked_fill(input_padding_mask[..., None], float(0))
+        value = value.view(n, len_in, self.n_heads, self.d_model // self.n_heads)
+        offsets = self.sampling_offsets(query).view(
+            n, len_q, self.n_heads, self.n_levels, self.n_points, 2)
+        weights = self.attention_weights(query).view(
+            n, len_q, self.n_heads, self.n_levels * self.n_points)
+        weights = F.softmax(weights, -1).view(n, len_q, self.n_heads, self.n_levels, self.n_points)
+        locations = self._sampling_locations(reference_points, offsets, input_spatial_shapes)
+
+        if value.dtype == torch.float16:
+            # models/dino/ops/modules/ms_deform_attn.py:124-131: half goes through fp32 and back
+            out = MSDeformAttnFunction.apply(value.float(), input_spatial_shapes, input_level_start_index,
+                                             locations.float(), weights.float(), self.im2col_step)
+            out = out.to(torch.float16)
+        else:
+            if locations.dtype != weights.dtype:
+                locations = locations.to(weights.dtype)
+            out = MSDeformAttnFunction.apply(value, input_spatial_shapes, input_level_start_index,
+                                             locations.contiguous(), weights, self.im2col_step)
+        return self.output_proj(out)
