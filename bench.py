@@ -162,7 +162,7 @@ def run_reference(args):
     return 0
 
 
-def time_device_steps(torch, cabi, wl, sets, bufs, kind, steps, warmup, per_kernel=True):
+def time_device_steps(torch, cabi, wl, sets, bufs, kind, steps, warmup, per_kernel=True, bf16_direct=False):
     """K steps of memset(grad_value) + fwd + bwd on the current stream.  Returns total ms and the
     per-kernel mean durations (CUDA events on the launching stream)."""
     dims = wl.dims()
@@ -170,7 +170,14 @@ def time_device_steps(torch, cabi, wl, sets, bufs, kind, steps, warmup, per_kern
 
     def step(i, ev=None):
         x = sets[i % len(sets)]
-        bufs["gv"].zero_()
+        scratch = None
+        if kind == "bf16" and not bf16_direct:
+            if "scratch" not in bufs:
+                bufs["scratch"] = torch.zeros(bufs["gv"].shape, device="cuda", dtype=torch.float32)
+            scratch = bufs["scratch"]
+            scratch.zero_()          # fp32 accumulation buffer; grad_value itself is fully overwritten
+        else:
+            bufs["gv"].zero_()
         if ev:
             ev[0].record()
         cabi.forward(kind, x["value"].data_ptr(), x["shapes"].data_ptr(), x["lsi"].data_ptr(), x["loc"].data_ptr(),
@@ -179,7 +186,8 @@ def time_device_steps(torch, cabi, wl, sets, bufs, kind, steps, warmup, per_kern
             ev[1].record()
         cabi.backward(kind, x["grad_out"].data_ptr(), x["value"].data_ptr(), x["shapes"].data_ptr(),
                       x["lsi"].data_ptr(), x["loc"].data_ptr(), x["aw"].data_ptr(), dims, bufs["gv"].data_ptr(),
-                      bufs["gl"].data_ptr(), bufs["ga"].data_ptr(), st)
+                      bufs["gl"].data_ptr(), bufs["ga"].data_ptr(), st,
+                      bf16_scratch_ptr=scratch.data_ptr() if scratch is not None else None)
         if ev:
             ev[2].record()
 
@@ -353,7 +361,7 @@ def extended(torch, cabi, args):
     res = {}
     steps, warmup = 30, 5
 
-    def run(name, kind, loc_dist=None, fwd_path=0, bwd_path=0, tag=None):
+    def run(name, kind, loc_dist=None, fwd_path=0, bwd_path=0, tag=None, bf16_direct=False):
         wl = WORKLOADS[name]
         vdt = torch.bfloat16 if kind == "bf16" else torch.float32
         sets = [make_inputs(wl, seed=s, device="cuda", value_dtype=vdt, loc_dist=loc_dist) for s in range(3)]
@@ -362,7 +370,8 @@ def extended(torch, cabi, args):
         cabi.set_option("fwd_path", fwd_path)
         cabi.set_option("bwd_path", bwd_path)
         try:
-            step, evs, t0, t1 = time_device_steps(torch, cabi, wl, sets, bufs, kind, steps, warmup)
+            step, evs, t0, t1 = time_device_steps(torch, cabi, wl, sets, bufs, kind, steps, warmup,
+                                                  bf16_direct=bf16_direct)
             t0.record()
             for i in range(steps):
                 step(i, evs[i])
@@ -388,7 +397,9 @@ def extended(torch, cabi, args):
     for name in ("c3_arctic_encoder", "c3_arctic_decoder", "c4_dino_decoder", "c4_dino_decoder_train"):
         run(name, "f32")
     run("c5_hires", "bf16")
+    run("c5_hires", "bf16", bf16_direct=True, tag="c5_hires:bf16:encoder:direct-bf16x2-red")
     run("c5_hires_contended", "bf16")
+    run("c5_hires_contended", "bf16", bf16_direct=True, tag="c5_hires_contended:bf16:contended:direct-bf16x2-red")
     run("c5_hires", "f32")
 
     # the reference's own kernels recompiled for sm_100a (informational; oracle/_ref is test infra)

@@ -85,12 +85,19 @@ int msda_bwd_f64(const double *grad_output, const double *value, const int64_t *
                  int batch, int spatial_size, int num_heads, int channels, int num_levels,
                  int num_query, int num_point,
                  double *grad_value, double *grad_sampling_loc, double *grad_attn_weight, void *stream);
-/* bf16 value and bf16 grad_value (accumulated with red.global.add.noftz.bf16x2), rest fp32. */
+/* bf16 value and bf16 grad_value, everything else fp32.  Two accumulation modes:
+ *   grad_value_scratch != NULL  (accurate, what the torch layer uses by default): an fp32 buffer of
+ *       batch*spatial_size*num_heads*channels floats, ZERO on entry; reductions go into it with
+ *       red.global.add.v4.f32 and it is rounded once into grad_value (which is then fully written);
+ *   grad_value_scratch == NULL  (direct): red.global.add.noftz.bf16x2 straight into grad_value, which
+ *       must be zero on entry.  Half the reduction bytes, but every add rounds the running sum to
+ *       bf16, so heavily hit rows drift (about 1.6e-2 relative L2 at the DETR-encoder shape). */
 int msda_bwd_bf16(const float *grad_output, const uint16_t *value, const int64_t *spatial_shapes,
                   const int64_t *level_start, const float *sampling_loc, const float *attn_weight,
                   int batch, int spatial_size, int num_heads, int channels, int num_levels,
                   int num_query, int num_point,
-                  uint16_t *grad_value, float *grad_sampling_loc, float *grad_attn_weight, void *stream);
+                  uint16_t *grad_value, float *grad_sampling_loc, float *grad_attn_weight,
+                  float *grad_value_scratch, void *stream);
 
 /* ---- parity probe ----------------------------------------------------------------------
  * Dumps, for every (n, q, m, l, p), what the kernels' shared sample-geometry routine decides:
@@ -128,9 +135,10 @@ int msda_host_fwd_bwd_f32(msda_host_plan *plan, const float *value, const int64_
                           float *grad_value, float *grad_sampling_loc, float *grad_attn_weight);
 
 /* ---- tuning / introspection --------------------------------------------------------------
- * Keys: "fwd_path", "bwd_path": 0 = automatic, 1 = force the any-shape kernels,
- * 2.. = a specific specialised variant.  Used by bench.py and the tests to
- * exercise every kernel on the same inputs.  Returns MSDA_OK or MSDA_ERR_BAD_OPTION. */
+ * Keys: "fwd_path", "bwd_path": 0 = automatic, 1 = force the any-shape kernels (used by bench.py
+ * and the tests to exercise every kernel on the same inputs); "bf16_direct_red": 0/1, read by the
+ * torch host layer to pick msda_bwd_bf16's accumulation mode (0 = fp32 scratch, the default).
+ * Returns MSDA_OK or MSDA_ERR_BAD_OPTION. */
 int msda_b200_set_option(const char *key, int value);
 int msda_b200_get_option(const char *key, int *value);
 /* Number of kernels this library has launched since load (all streams); bench.py's

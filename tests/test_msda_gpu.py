@@ -54,7 +54,7 @@ class Paths:
         cabi.set_option("bwd_path", 0)
 
 
-def run_cabi(kind, value, shapes, lsi, loc, aw, grad_out=None):
+def run_cabi(kind, value, shapes, lsi, loc, aw, grad_out=None, bf16_direct=False):
     """numpy in -> numpy out through msda_fwd_* / msda_bwd_* with device buffers."""
     tdt = {"f32": torch.float32, "f64": torch.float64, "bf16": torch.float32}[kind]
     vdt = torch.bfloat16 if kind == "bf16" else tdt
@@ -74,8 +74,13 @@ def run_cabi(kind, value, shapes, lsi, loc, aw, grad_out=None):
         gv = torch.zeros_like(v)
         gl = torch.full(lo.shape, float("nan"), device="cuda", dtype=tdt)
         ga = torch.full(a.shape, float("nan"), device="cuda", dtype=tdt)
+        scratch = None
+        if kind == "bf16" and not bf16_direct:
+            scratch = torch.zeros(v.shape, device="cuda", dtype=torch.float32)
+            gv.fill_(float("nan"))          # accurate mode fully overwrites grad_value
         cabi.backward(kind, g.data_ptr(), v.data_ptr(), sh.data_ptr(), ls.data_ptr(), lo.data_ptr(),
-                      a.data_ptr(), dims, gv.data_ptr(), gl.data_ptr(), ga.data_ptr(), st)
+                      a.data_ptr(), dims, gv.data_ptr(), gl.data_ptr(), ga.data_ptr(), st,
+                      bf16_scratch_ptr=scratch.data_ptr() if scratch is not None else None)
         res.update(grad_value=gv.float().cpu().numpy() if kind == "bf16" else gv.cpu().numpy(),
                    grad_loc=gl.cpu().numpy(), grad_aw=ga.cpu().numpy(), bwd_path=cabi.last_path(True))
     torch.cuda.synchronize()
@@ -215,19 +220,31 @@ def test_mid_size_f32(dist, Lq, forced):
     check_all(res, oracle(x["value"], x["shapes"], x["lsi"], x["loc"], x["aw"], x["grad_out"]))
 
 
+@pytest.mark.parametrize("direct", [False, True], ids=["f32acc", "direct-bf16x2"])
 @pytest.mark.parametrize("dist,Lq", [("encoder", MID_S), ("twostage", 300)])
-def test_mid_size_bf16(dist, Lq):
+def test_mid_size_bf16(dist, Lq, direct):
     wl = Workload("mid", 2, MID_LEVELS, Lq, loc_dist=dist)
     x = np_inputs(wl, 4)
     v_bf16 = torch.from_numpy(x["value"]).to(torch.bfloat16)
     v_round = v_bf16.float().numpy()                      # what the kernel actually reads
-    res = run_cabi("bf16", v_round, x["shapes"], x["lsi"], x["loc"], x["aw"], x["grad_out"])
+    res = run_cabi("bf16", v_round, x["shapes"], x["lsi"], x["loc"], x["aw"], x["grad_out"], bf16_direct=direct)
     ref = oracle(v_round, x["shapes"], x["lsi"], x["loc"], x["aw"], x["grad_out"])
-    assert res["fwd_path"] == "fwd_d32_bf16" and res["bwd_path"] == "bwd_d32_bf16"
+    assert res["fwd_path"] == "fwd_d32_bf16"
+    assert res["bwd_path"] == ("bwd_d32_bf16" if direct else "bwd_d32_bf16_f32acc")
     close(res["out"], ref["out"], FWD_RTOL)               # same rounded inputs -> fp32-level agreement
     close(res["grad_loc"], ref["grad_loc"], GRAD_RTOL)
     close(res["grad_aw"], ref["grad_aw"], GRAD_RTOL)
-    close(res["grad_value"], ref["grad_value"], BF16_RTOL * 4 if dist == "encoder" else BF16_RTOL)
+    gv, gv_ref = res["grad_value"].astype(np.float64), ref["grad_value"]
+    l2 = np.linalg.norm(gv - gv_ref) / np.linalg.norm(gv_ref)
+    worst = np.abs(gv - gv_ref).max() / np.abs(gv_ref).max()
+    print(f"bf16 grad_value {dist} direct={direct}: rel-L2 {l2:.3e}, worst/max {worst:.3e}")
+    if not direct:
+        # default bf16 mode: fp32 accumulation, ONE rounding to bf16 at the end -> the stated 1e-2
+        close(res["grad_value"], ref["grad_value"], BF16_RTOL)
+    else:
+        # direct red.global.add.noftz.bf16x2: every add rounds the running sum to 8 bits, heavily hit
+        # rows drift; documented looser bound (include/msda_b200.h), not the north_star tolerance.
+        assert l2 < 5e-2 and worst < 0.25, (l2, worst)
     # and against the unrounded value: the stated bf16 tolerance
     ref_full = oracle(x["value"], x["shapes"], x["lsi"], x["loc"], x["aw"], x["grad_out"])
     close(res["out"], ref_full["out"], BF16_RTOL)
@@ -317,8 +334,10 @@ def _full_size(wl, kind="f32", seed=0):
     gv = torch.zeros_like(t["value"])
     gl = torch.empty_like(t["loc"])
     ga = torch.empty_like(t["aw"])
+    scratch = torch.zeros(t["value"].shape, device="cuda") if kind == "bf16" else None
     cabi.backward(kind, t["grad_out"].data_ptr(), t["value"].data_ptr(), t["shapes"].data_ptr(), t["lsi"].data_ptr(),
-                  t["loc"].data_ptr(), t["aw"].data_ptr(), dims, gv.data_ptr(), gl.data_ptr(), ga.data_ptr(), st)
+                  t["loc"].data_ptr(), t["aw"].data_ptr(), dims, gv.data_ptr(), gl.data_ptr(), ga.data_ptr(), st,
+                  bf16_scratch_ptr=scratch.data_ptr() if scratch is not None else None)
     torch.cuda.synchronize()
     return t, out, gv, gl, ga
 
@@ -369,14 +388,14 @@ def test_full_size_c2_grad_value_vs_oracle():
 def test_full_size_c5_bf16_properties():
     wl = WORKLOADS["c5_hires"]
     t, out, gv, gl, ga = _full_size(wl, kind="bf16")
-    assert cabi.last_path(False) == "fwd_d32_bf16" and cabi.last_path(True) == "bwd_d32_bf16"
+    assert cabi.last_path(False) == "fwd_d32_bf16" and cabi.last_path(True) == "bwd_d32_bf16_f32acc"
     g = t["grad_out"].view_as(out).double()
     lhs = float((out.double() * g).sum())
     rhs_w = float((t["aw"].double() * ga.double()).sum())
     scale = float((out.double() * g).abs().sum())
     assert abs(lhs - rhs_w) < 1e-5 * scale
-    rhs_v = float((t["value"].double() * gv.double()).sum())        # bf16-accumulated
-    assert abs(lhs - rhs_v) < 2e-2 * scale
+    rhs_v = float((t["value"].double() * gv.double()).sum())        # grad_value rounded once to bf16
+    assert abs(lhs - rhs_v) < 1e-3 * scale
     gen = torch.Generator().manual_seed(1)
     idx = torch.randperm(wl.Lq, generator=gen)[:64].sort().values
     cpu = {k: v.cpu() for k, v in t.items()}
@@ -438,7 +457,7 @@ def test_function_dtype_policy():
         assert cabi.last_path(False) == "fwd_d32_bf16"
         assert torch.allclose(out_n, out_b, rtol=1e-5, atol=1e-5)
         out_n.backward(x["grad_out"])
-        assert vb.grad.dtype == torch.bfloat16 and cabi.last_path(True) == "bwd_d32_bf16"
+        assert vb.grad.dtype == torch.bfloat16 and cabi.last_path(True) == "bwd_d32_bf16_f32acc"
     finally:
         F.set_bf16_value_mode(False)
     assert torch.allclose(out_b, base, rtol=2e-2, atol=2e-2)

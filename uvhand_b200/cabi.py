@@ -12,7 +12,8 @@ import os
 from ctypes import c_char_p, c_int, c_int64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libmsda_b200.so")
+# MSDA_B200_LIB lets tools/ time experimental builds of the same ABI; the default is the in-tree build.
+LIB_PATH = os.environ.get("MSDA_B200_LIB") or os.path.join(_HERE, "lib", "libmsda_b200.so")
 
 # every symbol include/msda_b200.h declares (tests check that the library exports exactly these)
 SYMBOLS = (
@@ -51,8 +52,9 @@ def lib() -> ctypes.CDLL:
         seven = [c_int] * 7
         for name in ("msda_fwd_f32", "msda_fwd_f64", "msda_fwd_bf16"):
             getattr(L, name).argtypes = [c_void_p] * 5 + seven + [c_void_p, c_void_p]
-        for name in ("msda_bwd_f32", "msda_bwd_f64", "msda_bwd_bf16"):
+        for name in ("msda_bwd_f32", "msda_bwd_f64"):
             getattr(L, name).argtypes = [c_void_p] * 6 + seven + [c_void_p] * 4
+        L.msda_bwd_bf16.argtypes = [c_void_p] * 6 + seven + [c_void_p] * 5
         L.msda_sample_index_f32.argtypes = [c_void_p, c_void_p] + [c_int] * 5 + [c_void_p] * 4
         L.msda_host_plan_create.argtypes = [ctypes.POINTER(c_void_p), c_int] + seven
         L.msda_host_plan_destroy.argtypes = [c_void_p]
@@ -103,10 +105,16 @@ def forward(kind: str, value_ptr, shapes_ptr, lsi_ptr, loc_ptr, aw_ptr, dims, ou
 
 
 def backward(kind: str, go_ptr, value_ptr, shapes_ptr, lsi_ptr, loc_ptr, aw_ptr, dims,
-             gv_ptr, gl_ptr, ga_ptr, stream=0) -> None:
+             gv_ptr, gl_ptr, ga_ptr, stream=0, bf16_scratch_ptr=None) -> None:
+    """bf16: `bf16_scratch_ptr` (zeroed fp32 buffer, value-sized) selects the accurate accumulation
+    mode; None = direct bf16x2 reductions into a zeroed grad_value."""
     fn = getattr(lib(), "msda_bwd_" + _SUFFIX[kind])
-    check(fn(go_ptr, value_ptr, shapes_ptr, lsi_ptr, loc_ptr, aw_ptr, *dims, gv_ptr, gl_ptr, ga_ptr, stream),
-          "msda_bwd_" + kind)
+    if kind == "bf16":
+        rc = fn(go_ptr, value_ptr, shapes_ptr, lsi_ptr, loc_ptr, aw_ptr, *dims, gv_ptr, gl_ptr, ga_ptr,
+                bf16_scratch_ptr, stream)
+    else:
+        rc = fn(go_ptr, value_ptr, shapes_ptr, lsi_ptr, loc_ptr, aw_ptr, *dims, gv_ptr, gl_ptr, ga_ptr, stream)
+    check(rc, "msda_bwd_" + kind)
 
 
 def sample_index(shapes_ptr, loc_ptr, N, Lq, M, L, P, h_ptr, w_ptr, mask_ptr, stream=0) -> None:

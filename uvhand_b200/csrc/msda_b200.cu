@@ -21,6 +21,7 @@ using namespace msda;
 
 std::atomic<int> g_fwd_path{0};
 std::atomic<int> g_bwd_path{0};
+std::atomic<int> g_bf16_direct{0};
 std::atomic<long long> g_launches{0};
 const char* g_last_path[2] = {"none", "none"};
 
@@ -59,10 +60,10 @@ int finish_launch(int n_launched) {
   return e == cudaSuccess ? MSDA_OK : (int)e;
 }
 
-// The specialised kernels address value rows with 32-bit chunk offsets inside one sample.
+// The specialised kernels carry (token * M) row offsets in a signed 28-bit field.
 bool d32_eligible(int S, int M, int D, int L, int P) {
   return D == 32 && L >= 1 && L <= kMaxLevelsD32 && L * P >= 1 && L * P <= kMaxLPD32 &&
-         (long long)S * M * 8 < (1ll << 31);
+         (long long)S * M < kMaxTokenHeadsD32;
 }
 
 int d32_grid(long long n_items) {
@@ -74,7 +75,7 @@ int d32_grid(long long n_items) {
   return (int)ctas;
 }
 
-size_t d32_smem(int LP) { return (size_t)kD32Warps * 2 * kItemsPerWarp * LP * 16; }
+size_t d32_smem(int LP) { return (size_t)kD32Warps * kItemsPerWarp * rec_stride(LP) * 16; }
 
 int generic_grid(long long n_items) {
   long long ctas = (n_items + (kGenericThreads / kWarp) - 1) / (kGenericThreads / kWarp);
@@ -88,22 +89,22 @@ template <typename VT>
 int launch_fwd_d32(const D32Params& p, cudaStream_t st) {
   const int LP = p.L * p.P;
   const int grid = d32_grid(p.n_items);
-  if (LP == 16) {
-    fwd_d32_kernel<VT, 16><<<grid, kD32Threads, d32_smem(LP), st>>>(p);
+  if (p.L == 4 && p.P == 4) {
+    fwd_d32_kernel<VT, 4, 4><<<grid, kD32Threads, d32_smem(LP), st>>>(p);
   } else {
-    fwd_d32_kernel<VT, 0><<<grid, kD32Threads, d32_smem(LP), st>>>(p);
+    fwd_d32_kernel<VT, 0, 0><<<grid, kD32Threads, d32_smem(LP), st>>>(p);
   }
   return finish_launch(1);
 }
 
-template <typename VT>
+template <typename VT, typename GT>
 int launch_bwd_d32(const D32Params& p, cudaStream_t st) {
   const int LP = p.L * p.P;
   const int grid = d32_grid(p.n_items);
-  if (LP == 16) {
-    bwd_d32_kernel<VT, 16><<<grid, kD32Threads, d32_smem(LP), st>>>(p);
+  if (p.L == 4 && p.P == 4) {
+    bwd_d32_kernel<VT, GT, 4, 4><<<grid, kD32Threads, d32_smem(LP), st>>>(p);
   } else {
-    bwd_d32_kernel<VT, 0><<<grid, kD32Threads, d32_smem(LP), st>>>(p);
+    bwd_d32_kernel<VT, GT, 0, 0><<<grid, kD32Threads, d32_smem(LP), st>>>(p);
   }
   return finish_launch(1);
 }
@@ -168,6 +169,11 @@ int msda_b200_set_option(const char* key, int value) {
     g_bwd_path.store(value);
     return MSDA_OK;
   }
+  if (!strcmp(key, "bf16_direct_red")) {
+    if (value < 0 || value > 1) return MSDA_ERR_BAD_OPTION;
+    g_bf16_direct.store(value);
+    return MSDA_OK;
+  }
   return MSDA_ERR_BAD_OPTION;
 }
 
@@ -175,6 +181,7 @@ int msda_b200_get_option(const char* key, int* value) {
   if (!key || !value) return MSDA_ERR_BAD_OPTION;
   if (!strcmp(key, "fwd_path")) { *value = g_fwd_path.load(); return MSDA_OK; }
   if (!strcmp(key, "bwd_path")) { *value = g_bwd_path.load(); return MSDA_OK; }
+  if (!strcmp(key, "bf16_direct_red")) { *value = g_bf16_direct.load(); return MSDA_OK; }
   return MSDA_ERR_BAD_OPTION;
 }
 
@@ -283,7 +290,7 @@ int msda_bwd_f32(const float* go, const float* value, const int64_t* shapes, con
     p.N = N; p.S = S; p.M = M; p.L = L; p.Lq = Lq; p.P = P;
     p.n_items = (long long)N * Lq * M;
     g_last_path[1] = "bwd_d32_f32";
-    return launch_bwd_d32<float>(p, st);
+    return launch_bwd_d32<float, float>(p, st);
   }
   g_last_path[1] = "bwd_generic_f32";
   return bwd_any<float>(go, value, shapes, lsi, loc, aw, N, S, M, D, L, Lq, P, gv, gl, ga, st);
@@ -306,22 +313,39 @@ int msda_bwd_f64(const double* go, const double* value, const int64_t* shapes, c
 
 int msda_bwd_bf16(const float* go, const uint16_t* value, const int64_t* shapes, const int64_t* lsi,
                   const float* loc, const float* aw, int N, int S, int M, int D, int L, int Lq, int P,
-                  uint16_t* gv, float* gl, float* ga, void* stream) {
+                  uint16_t* gv, float* gl, float* ga, float* gv_scratch, void* stream) {
   int rc = check_dims(N, S, M, D, L, Lq, P);
   if (rc) return rc;
   if (nothing_to_do(N, M, D, Lq) || L == 0 || P == 0 || S == 0) return MSDA_OK;
   if (!go || !value || !shapes || !lsi || !loc || !aw || !gv || !gl || !ga) return MSDA_ERR_NULL_POINTER;
   if (!d32_eligible(S, M, D, L, P)) return MSDA_ERR_UNSUPPORTED;
   if (!aligned(go, 16) || !aligned(value, 8) || !aligned(gv, 8) || !aligned(loc, 8) || !aligned(aw, 4) ||
-      !aligned(gl, 8) || !aligned(ga, 4) || !aligned(shapes, 8) || !aligned(lsi, 8))
+      !aligned(gl, 8) || !aligned(ga, 4) || !aligned(shapes, 8) || !aligned(lsi, 8) ||
+      (gv_scratch && !aligned(gv_scratch, 16)))
     return MSDA_ERR_MISALIGNED;
+  cudaStream_t st = (cudaStream_t)stream;
   D32Params p{};
   p.value = value; p.shapes = shapes; p.lsi = lsi; p.loc = loc; p.aw = aw; p.grad_out = go;
-  p.grad_value = gv; p.grad_loc = gl; p.grad_aw = ga;
+  p.grad_loc = gl; p.grad_aw = ga;
   p.N = N; p.S = S; p.M = M; p.L = L; p.Lq = Lq; p.P = P;
   p.n_items = (long long)N * Lq * M;
+  if (gv_scratch) {
+    // accurate mode: fp32 reductions into the scratch, one rounding to bf16 at the end
+    p.grad_value = gv_scratch;
+    g_last_path[1] = "bwd_d32_bf16_f32acc";
+    rc = launch_bwd_d32<__nv_bfloat16, float>(p, st);
+    if (rc) return rc;
+    const long long n4 = (long long)N * S * M * 8;
+    long long blocks = (n4 + 255) / 256;
+    const long long cap = (long long)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    f32_to_bf16_kernel<<<(int)blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(gv_scratch),
+                                                   reinterpret_cast<uint2*>(gv), n4);
+    return finish_launch(1);
+  }
+  p.grad_value = gv;
   g_last_path[1] = "bwd_d32_bf16";
-  return launch_bwd_d32<__nv_bfloat16>(p, (cudaStream_t)stream);
+  return launch_bwd_d32<__nv_bfloat16, __nv_bfloat16>(p, st);
 }
 
 // ---- parity probe -------------------------------------------------------------------------

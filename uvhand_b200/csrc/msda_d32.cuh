@@ -10,13 +10,19 @@
 //     M % 4 == 0), whose sampling locations / weights / outputs are contiguous in memory:
 //     every streaming access of the warp is one fully coalesced segment.
 //
-// Two phases per warp pass, separated only by __syncwarp (no block barrier anywhere):
+// Two phases per warp pass, separated only by __syncwarp (no block barrier in the loop):
 //   A  "geometry": the 4*L*P samples of the pass are spread over the 32 lanes (one thread per
-//      sample, no redundancy); each computes sample_geom(), the four corner offsets and the
-//      four bilinear weights, and parks them as a 32 B record in the warp's private slice of
-//      shared memory.
-//   B  "gather": every 8-lane group walks its item's L*P records (two broadcast LDS.128 per
-//      sample), issues the 4 corner row loads, and accumulates.
+//      sample, no redundancy); each runs sample_geom() and parks a 16 B record
+//          { row offset of corner (h_low, w_low) << 4 | corner mask,  f0, f1, f2 }
+//      in the warp's private slice of shared memory.  Group slices are padded by one record so
+//      that the four groups' broadcast reads fall into distinct banks.
+//   B  "gather": every 8-lane group walks its item's L*P records (ONE broadcast LDS.128 per
+//      sample), rebuilds the four bilinear weights (5 flops) and corner offsets (3 adds), issues
+//      the 4 corner row loads and accumulates.
+//
+// Both kernels are bound by the SM's load/store data path (one 128 B row per wavefront) and,
+// for the backward, by the SM->L2 reduction path; everything else is arranged to stay out of
+// their way (profiles/ has the ncu evidence).
 //
 // The reference instead recomputes all of phase A in each of the 32 channel threads and issues
 // 64 predicated scalar loads per thread (cuh:272-296); its backward adds 2*L*P block barriers
@@ -28,16 +34,21 @@
 
 namespace msda {
 
+// Minimum resident CTAs per SM the compiler must leave room for (register cap = 65536 / (256*n)).
+#ifndef MSDA_FWD_MINB
+#define MSDA_FWD_MINB 6
+#endif
+#ifndef MSDA_BWD_MINB
+#define MSDA_BWD_MINB 4
+#endif
+
 constexpr int kD32Warps = 8;                  // warps per CTA
 constexpr int kD32Threads = kD32Warps * kWarp;
 constexpr int kItemsPerWarp = 4;              // 8 lanes per item
 constexpr int kMaxLevelsD32 = 8;
 constexpr int kMaxLPD32 = 32;                 // L*P limit of the specialised kernels
-
-struct __align__(16) CornerRec {
-  float w[4];  // forward: bilinear weight * attention weight; backward: (lh, lw, a, unused)
-  int off[4];  // offset of each corner row in Chunk units relative to the item's base; <0 = outside
-};
+// Row offsets are carried as (token*M) in a signed 28-bit field.
+constexpr long long kMaxTokenHeadsD32 = 1ll << 27;
 
 struct LevelTab {
   int H[kMaxLevelsD32], W[kMaxLevelsD32], start[kMaxLevelsD32];
@@ -58,6 +69,8 @@ struct D32Params {
   long long n_items;
 };
 
+__host__ __device__ constexpr int rec_stride(int LP) { return LP | 1; }  // odd => conflict-free groups
+
 __device__ __forceinline__ void load_level_tab(LevelTab& tab, const D32Params& p) {
   if (threadIdx.x < p.L) {
     tab.H[threadIdx.x] = (int)p.shapes[2 * threadIdx.x];
@@ -67,57 +80,45 @@ __device__ __forceinline__ void load_level_tab(LevelTab& tab, const D32Params& p
   __syncthreads();
 }
 
-// Phase A for one sample.  kBackward selects what goes into rec.w.
+// Phase A for one sample.
+//   forward : f = (a*hh, a*lh, lw)      backward : f = (lh, lw, a)
+// A rejected sample gets mask 0 and zero payload: phase B then loads nothing and adds zero.
 template <bool kBackward>
-__device__ __forceinline__ void make_record(CornerRec& rec, float x, float y, float a, int H, int W,
-                                            int start, int M) {
+__device__ __forceinline__ int4 make_record(float x, float y, float a, int H, int W, int start, int M) {
   SampleGeom<float> g;
-  if (!sample_geom<float>(x, y, H, W, g)) {
-    rec.w[0] = rec.w[1] = rec.w[2] = rec.w[3] = 0.f;
-    rec.off[0] = rec.off[1] = rec.off[2] = rec.off[3] = -1;
-    return;
-  }
-  const int chunks_per_token = M * 8;  // 8 chunks of 4 channels per head row
-  const int r00 = (start + g.h_low * W + g.w_low) * chunks_per_token;
-  rec.off[0] = (g.mask & 1u) ? r00 : -1;
-  rec.off[1] = (g.mask & 2u) ? r00 + chunks_per_token : -1;
-  rec.off[2] = (g.mask & 4u) ? r00 + W * chunks_per_token : -1;
-  rec.off[3] = (g.mask & 8u) ? r00 + (W + 1) * chunks_per_token : -1;
+  if (!sample_geom<float>(x, y, H, W, g)) return make_int4(0, 0, 0, 0);
+  const int row_m = (start + g.h_low * W + g.w_low) * M;  // may be negative at the top/left border
+  int4 r;
+  r.x = row_m * 16 + (int)g.mask;
   if (kBackward) {
-    rec.w[0] = g.lh;
-    rec.w[1] = g.lw;
-    rec.w[2] = a;
-    rec.w[3] = 0.f;
+    r.y = __float_as_int(g.lh);
+    r.z = __float_as_int(g.lw);
+    r.w = __float_as_int(a);
   } else {
-    const float hh = 1.f - g.lh, hw = 1.f - g.lw;
-    rec.w[0] = hh * hw * a;
-    rec.w[1] = hh * g.lw * a;
-    rec.w[2] = g.lh * hw * a;
-    rec.w[3] = g.lh * g.lw * a;
+    r.y = __float_as_int(a * (1.f - g.lh));
+    r.z = __float_as_int(a * g.lh);
+    r.w = __float_as_int(g.lw);
   }
+  return r;
 }
 
 // Phase A for the whole warp pass: 4*LP samples over 32 lanes, coalesced loc / weight loads.
-//
-// Records are parked as two planes (weights, offsets) so that the 16 B stores of consecutive
-// lanes and the broadcast loads of phase B are both free of bank conflicts.
 template <bool kBackward>
-__device__ __forceinline__ void geometry_phase(float4* rec_w, int4* rec_o, const D32Params& p,
-                                               const LevelTab& tab, long long item0, int LP, int lane) {
+__device__ __forceinline__ void geometry_phase(int4* warp_recs, const D32Params& p, const LevelTab& tab,
+                                               long long item0, int LP, int lane) {
   const int n_samples = kItemsPerWarp * LP;
+  const int stride = rec_stride(LP);
   const long long s_base = item0 * LP;
   const long long s_end = p.n_items * LP;
   for (int s = lane; s < n_samples; s += kWarp) {
     const long long gs = s_base + s;
     if (gs >= s_end) break;
-    const int ls = s % LP;
+    const int grp = s / LP;
+    const int ls = s - grp * LP;
     const int l = ls / p.P;
     const float2 xy = ld_stream(reinterpret_cast<const float2*>(p.loc) + gs);
     const float a = ld_stream(p.aw + gs);
-    CornerRec rec;
-    make_record<kBackward>(rec, xy.x, xy.y, a, tab.H[l], tab.W[l], tab.start[l], p.M);
-    rec_w[s] = make_float4(rec.w[0], rec.w[1], rec.w[2], rec.w[3]);
-    rec_o[s] = make_int4(rec.off[0], rec.off[1], rec.off[2], rec.off[3]);
+    warp_recs[grp * stride + ls] = make_record<kBackward>(xy.x, xy.y, a, tab.H[l], tab.W[l], tab.start[l], p.M);
   }
 }
 
@@ -130,12 +131,25 @@ __device__ __forceinline__ void fma4(float4& acc, float w, const float4& v) {
 __device__ __forceinline__ float dot4(const float4& a, const float4& b) {
   return fmaf(a.w, b.w, fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x)));
 }
+__device__ __forceinline__ float4 scale4(float s, const float4& v) {
+  return make_float4(s * v.x, s * v.y, s * v.z, s * v.w);
+}
+
+// Per-level row stride W*M, in registers when the level count is a compile-time constant.
+template <int kL>
+struct LevelStride {
+  int wm[kL > 0 ? kL : 1];
+  __device__ __forceinline__ void init(const LevelTab& tab, int M) {
+#pragma unroll
+    for (int l = 0; l < (kL > 0 ? kL : 1); ++l) wm[l] = tab.W[l] * M;
+  }
+};
 
 // ---------------------------------------------------------------------------------------------
 // Forward
 // ---------------------------------------------------------------------------------------------
-template <typename VT, int kLP>  // kLP = compile-time L*P (0: runtime)
-__global__ void __launch_bounds__(kD32Threads)
+template <typename VT, int kL, int kP>  // compile-time levels / points (0,0: runtime)
+__global__ void __launch_bounds__(kD32Threads, MSDA_FWD_MINB)
 fwd_d32_kernel(const D32Params p) {
   using C = Chunk<VT>;
   using Vec = typename C::Vec;
@@ -143,40 +157,56 @@ fwd_d32_kernel(const D32Params p) {
   __shared__ LevelTab tab;
   load_level_tab(tab, p);
 
-  const int LP = kLP ? kLP : p.L * p.P;
+  constexpr bool kStatic = kL > 0;
+  const int P = kStatic ? kP : p.P;
+  const int LP = kStatic ? kL * kP : p.L * p.P;
+  const int stride = rec_stride(LP);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int group = lane >> 3, sub = lane & 7;
-  float4* rec_w = reinterpret_cast<float4*>(smem_raw) + warp * (2 * kItemsPerWarp * LP);
-  int4* rec_o = reinterpret_cast<int4*>(rec_w + kItemsPerWarp * LP);
-  const float4* my_w = rec_w + group * LP;
-  const int4* my_o = rec_o + group * LP;
+  int4* warp_recs = reinterpret_cast<int4*>(smem_raw) + warp * (kItemsPerWarp * stride);
+  const int4* my_recs = warp_recs + group * stride;
+  const int M = p.M;
+  LevelStride<kL> lv;
+  if (kStatic) lv.init(tab, M);
 
   const long long n_pass = (p.n_items + kItemsPerWarp - 1) / kItemsPerWarp;
   const long long pass_stride = (long long)gridDim.x * kD32Warps;
   for (long long pass = (long long)blockIdx.x * kD32Warps + warp; pass < n_pass; pass += pass_stride) {
     const long long item0 = pass * kItemsPerWarp;
-    geometry_phase<false>(rec_w, rec_o, p, tab, item0, LP, lane);
+    geometry_phase<false>(warp_recs, p, tab, item0, LP, lane);
     __syncwarp();
 
     const long long item = item0 + group;
     if (item < p.n_items) {
-      const int m = (int)(item % p.M);
-      const int b = (int)(item / ((long long)p.M * p.Lq));
-      const Vec* vb = reinterpret_cast<const Vec*>(p.value) + ((long long)b * p.S * p.M + m) * 8 + sub;
+      const int m = (int)(item % M);
+      const int b = (int)(item / ((long long)M * p.Lq));
+      // Chunk units: one token-head row is 8 chunks; row_m counts token*M, so row = row_m * 8.
+      const Vec* vb = reinterpret_cast<const Vec*>(p.value) + ((long long)b * p.S * M + m) * 8 + sub;
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-      for (int s = 0; s < LP; ++s) {
-        const float4 w = my_w[s];
-        const int4 o = my_o[s];
-        float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0, v2 = v0, v3 = v0;
-        if (o.x >= 0) v0 = C::load(vb + o.x);
-        if (o.y >= 0) v1 = C::load(vb + o.y);
-        if (o.z >= 0) v2 = C::load(vb + o.z);
-        if (o.w >= 0) v3 = C::load(vb + o.w);
-        fma4(acc, w.x, v0);
-        fma4(acc, w.y, v1);
-        fma4(acc, w.z, v2);
-        fma4(acc, w.w, v3);
+#pragma unroll
+      for (int l = 0; l < (kStatic ? kL : 1); ++l) {
+        const int s_lo = kStatic ? l * kP : 0;
+        const int s_hi = kStatic ? (l + 1) * kP : LP;
+#pragma unroll
+        for (int s = s_lo; s < s_hi; ++s) {
+          const int4 r = my_recs[s];
+          const int wm = kStatic ? lv.wm[l] : tab.W[s / P] * M;
+          const int row = r.x >> 4;
+          const float ah = __int_as_float(r.y), al = __int_as_float(r.z), lw = __int_as_float(r.w);
+          const float w2 = ah * lw, w4 = al * lw;
+          const float w1 = ah - w2, w3 = al - w4;   // a*hh*(1-lw), a*lh*(1-lw)
+          const Vec* r0 = vb + (long long)row * 8;
+          const Vec* r1 = r0 + (long long)wm * 8;
+          float4 v1 = make_float4(0.f, 0.f, 0.f, 0.f), v2 = v1, v3 = v1, v4 = v1;
+          if (r.x & 1) v1 = C::load(r0);
+          if (r.x & 2) v2 = C::load(r0 + M * 8);
+          if (r.x & 4) v3 = C::load(r1);
+          if (r.x & 8) v4 = C::load(r1 + M * 8);
+          fma4(acc, w1, v1);
+          fma4(acc, w2, v2);
+          fma4(acc, w3, v3);
+          fma4(acc, w4, v4);
+        }
       }
       st_stream(reinterpret_cast<float4*>(p.out) + item * 8 + sub, acc);
     }
@@ -194,74 +224,150 @@ __device__ __forceinline__ float group8_sum(float v) {
   return v;
 }
 
-template <typename VT, int kLP>
-__global__ void __launch_bounds__(kD32Threads)
+// Sum four per-lane values over the 8 lanes of a group with 4 shuffles instead of 12: after the
+// call, lane `sub` holds the group total of v[sub >> 1] (both lanes of a pair hold the same one).
+__device__ __forceinline__ float group8_sum4(const float (&v)[4], int sub) {
+  const bool hi4 = sub & 4, hi2 = sub & 2;
+  const float keep0 = hi4 ? v[2] : v[0], send0 = hi4 ? v[0] : v[2];
+  const float keep1 = hi4 ? v[3] : v[1], send1 = hi4 ? v[1] : v[3];
+  const float r0 = keep0 + __shfl_xor_sync(kFull, send0, 4);
+  const float r1 = keep1 + __shfl_xor_sync(kFull, send1, 4);
+  const float keep = hi2 ? r1 : r0, send = hi2 ? r0 : r1;
+  float t = keep + __shfl_xor_sync(kFull, send, 2);
+  t += __shfl_xor_sync(kFull, t, 1);
+  return t;
+}
+
+// One sample of the backward for one lane: 4 corner loads, 4 vector reductions into grad_value,
+// and this lane's partial sums for grad_attn_weight / grad_loc.
+template <typename VT, typename GT>
+__device__ __forceinline__ void bwd_sample(const int4 r, const typename Chunk<VT>::Vec* vb,
+                                           typename Chunk<GT>::Vec* gvb, const float4& g, int M, int wm,
+                                           float Wf, float Hf, bool live, float& pa, float& px, float& py) {
+  using C = Chunk<VT>;
+  using G = Chunk<GT>;
+  const int row = r.x >> 4;
+  const float lh = __int_as_float(r.y), lw = __int_as_float(r.z), a = __int_as_float(r.w);
+  const float hh = 1.f - lh, hw = 1.f - lw;
+  const float w1 = hh * hw, w2 = hh * lw, w3 = lh * hw, w4 = lh * lw;
+  const long long o0 = (long long)row * 8, o1 = o0 + (long long)wm * 8;
+  const int dx = M * 8;
+  float4 v1 = make_float4(0.f, 0.f, 0.f, 0.f), v2 = v1, v3 = v1, v4 = v1;
+  const bool ok1 = live && (r.x & 1), ok2 = live && (r.x & 2), ok3 = live && (r.x & 4), ok4 = live && (r.x & 8);
+  if (ok1) v1 = C::load(vb + o0);
+  if (ok2) v2 = C::load(vb + o0 + dx);
+  if (ok3) v3 = C::load(vb + o1);
+  if (ok4) v4 = C::load(vb + o1 + dx);
+  const float4 t = scale4(a, g);  // top_grad * attn_weight (cuh:115)
+  if (ok1) G::red_add(gvb + o0, scale4(w1, t));
+  if (ok2) G::red_add(gvb + o0 + dx, scale4(w2, t));
+  if (ok3) G::red_add(gvb + o1, scale4(w3, t));
+  if (ok4) G::red_add(gvb + o1 + dx, scale4(w4, t));
+  const float d1 = dot4(g, v1), d2 = dot4(g, v2), d3 = dot4(g, v3), d4 = dot4(g, v4);
+  pa = w1 * d1 + w2 * d2 + w3 * d3 + w4 * d4;                    // cuh:156
+  px = (hh * (d2 - d1) + lh * (d4 - d3)) * a * Wf;               // cuh:157
+  py = (hw * (d3 - d1) + lw * (d4 - d2)) * a * Hf;               // cuh:158
+}
+
+// VT: storage type of value; GT: type grad_value is accumulated in (float: red.v4.f32 -- also used
+// for bf16 values accumulating into an fp32 scratch; __nv_bfloat16: red.v2.bf16x2 straight into a
+// bf16 grad_value, faster but every add rounds the running sum to 8 bits).
+template <typename VT, typename GT, int kL, int kP>
+__global__ void __launch_bounds__(kD32Threads, MSDA_BWD_MINB)
 bwd_d32_kernel(const D32Params p) {
   using C = Chunk<VT>;
   using Vec = typename C::Vec;
+  using GVec = typename Chunk<GT>::Vec;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ LevelTab tab;
   load_level_tab(tab, p);
 
-  const int LP = kLP ? kLP : p.L * p.P;
+  constexpr bool kStatic = kL > 0 && (kP % 4 == 0);
+  const int P = kStatic ? kP : p.P;
+  const int LP = kStatic ? kL * kP : p.L * p.P;
+  const int stride = rec_stride(LP);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int group = lane >> 3, sub = lane & 7;
-  float4* rec_w = reinterpret_cast<float4*>(smem_raw) + warp * (2 * kItemsPerWarp * LP);
-  int4* rec_o = reinterpret_cast<int4*>(rec_w + kItemsPerWarp * LP);
-  const float4* my_w = rec_w + group * LP;
-  const int4* my_o = rec_o + group * LP;
+  int4* warp_recs = reinterpret_cast<int4*>(smem_raw) + warp * (kItemsPerWarp * stride);
+  const int4* my_recs = warp_recs + group * stride;
+  const int M = p.M;
 
   const long long n_pass = (p.n_items + kItemsPerWarp - 1) / kItemsPerWarp;
   const long long pass_stride = (long long)gridDim.x * kD32Warps;
   for (long long pass = (long long)blockIdx.x * kD32Warps + warp; pass < n_pass; pass += pass_stride) {
     const long long item0 = pass * kItemsPerWarp;
-    geometry_phase<true>(rec_w, rec_o, p, tab, item0, LP, lane);
+    geometry_phase<true>(warp_recs, p, tab, item0, LP, lane);
     __syncwarp();
 
     // Groups past the end still take part in the shuffles (with zero data).
     const long long item = item0 + group;
     const bool live = item < p.n_items;
     const long long item_c = live ? item : (p.n_items - 1);
-    const int m = (int)(item_c % p.M);
-    const int b = (int)(item_c / ((long long)p.M * p.Lq));
-    const long long head_off = ((long long)b * p.S * p.M + m) * 8 + sub;
+    const int m = (int)(item_c % M);
+    const int b = (int)(item_c / ((long long)M * p.Lq));
+    const long long head_off = ((long long)b * p.S * M + m) * 8 + sub;
     const Vec* vb = reinterpret_cast<const Vec*>(p.value) + head_off;
-    Vec* gvb = reinterpret_cast<Vec*>(p.grad_value) + head_off;
+    GVec* gvb = reinterpret_cast<GVec*>(p.grad_value) + head_off;
     float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
     if (live) g = ld_stream(reinterpret_cast<const float4*>(p.grad_out) + item * 8 + sub);
+    float2* gl_out = reinterpret_cast<float2*>(p.grad_loc) + item_c * LP;
+    float* ga_out = p.grad_aw + item_c * LP;
 
-    for (int s = 0; s < LP; ++s) {
-      const float4 r = my_w[s];  // lh, lw, a
-      const int4 o = my_o[s];
-      const int l = s / p.P;
-      const float lh = r.x, lw = r.y, a = r.z;
-      const float hh = 1.f - lh, hw = 1.f - lw;
-      const float w1 = hh * hw, w2 = hh * lw, w3 = lh * hw, w4 = lh * lw;
-      float4 v1 = make_float4(0.f, 0.f, 0.f, 0.f), v2 = v1, v3 = v1, v4 = v1;
-      const bool ok1 = live && o.x >= 0, ok2 = live && o.y >= 0, ok3 = live && o.z >= 0,
-                 ok4 = live && o.w >= 0;
-      if (ok1) v1 = C::load(vb + o.x);
-      if (ok2) v2 = C::load(vb + o.y);
-      if (ok3) v3 = C::load(vb + o.z);
-      if (ok4) v4 = C::load(vb + o.w);
-      const float4 t = make_float4(g.x * a, g.y * a, g.z * a, g.w * a);
-      if (ok1) C::red_add(gvb + o.x, make_float4(w1 * t.x, w1 * t.y, w1 * t.z, w1 * t.w));
-      if (ok2) C::red_add(gvb + o.y, make_float4(w2 * t.x, w2 * t.y, w2 * t.z, w2 * t.w));
-      if (ok3) C::red_add(gvb + o.z, make_float4(w3 * t.x, w3 * t.y, w3 * t.z, w3 * t.w));
-      if (ok4) C::red_add(gvb + o.w, make_float4(w4 * t.x, w4 * t.y, w4 * t.z, w4 * t.w));
-      const float d1 = dot4(g, v1), d2 = dot4(g, v2), d3 = dot4(g, v3), d4 = dot4(g, v4);
-      float ga = w1 * d1 + w2 * d2 + w3 * d3 + w4 * d4;
-      float gx = (hh * (d2 - d1) + lh * (d4 - d3)) * a * (float)tab.W[l];
-      float gy = (hw * (d3 - d1) + lw * (d4 - d2)) * a * (float)tab.H[l];
-      ga = group8_sum(ga);
-      gx = group8_sum(gx);
-      gy = group8_sum(gy);
-      if (live && sub == (s & 7)) {
-        st_stream(reinterpret_cast<float2*>(p.grad_loc) + item * LP + s, make_float2(gx, gy));
-        st_stream(p.grad_aw + item * LP + s, ga);
+    if (kStatic) {
+      // 4 samples at a time: 12 partial sums reduced with 12 shuffles; lane pair (sub>>1) ends up
+      // with sample s0 + (sub>>1); the even lane stores grad_loc, the odd lane grad_attn_weight.
+#pragma unroll
+      for (int l = 0; l < (kStatic ? kL : 1); ++l) {
+        const int wm = tab.W[l] * M;
+        const float Wf = (float)tab.W[l], Hf = (float)tab.H[l];
+#pragma unroll
+        for (int q4 = 0; q4 < (kStatic ? kP / 4 : 1); ++q4) {
+          const int s0 = l * kP + q4 * 4;
+          float pa[4], px[4], py[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            bwd_sample<VT, GT>(my_recs[s0 + j], vb, gvb, g, M, wm, Wf, Hf, live, pa[j], px[j], py[j]);
+          const float ta = group8_sum4(pa, sub);
+          const float tx = group8_sum4(px, sub);
+          const float ty = group8_sum4(py, sub);
+          const int s = s0 + (sub >> 1);
+          if (live) {
+            if (sub & 1) st_stream(ga_out + s, ta);
+            else st_stream(gl_out + s, make_float2(tx, ty));
+          }
+        }
+      }
+    } else {
+      for (int s = 0; s < LP; ++s) {
+        const int l = s / P;
+        float pa, px, py;
+        bwd_sample<VT, GT>(my_recs[s], vb, gvb, g, M, tab.W[l] * M, (float)tab.W[l], (float)tab.H[l], live,
+                       pa, px, py);
+        pa = group8_sum(pa);
+        px = group8_sum(px);
+        py = group8_sum(py);
+        if (live && sub == (s & 7)) {
+          st_stream(gl_out + s, make_float2(px, py));
+          st_stream(ga_out + s, pa);
+        }
       }
     }
     __syncwarp();
+  }
+}
+
+// fp32 scratch -> bf16 grad_value (the accurate bf16 mode: one rounding at the end).
+__global__ void __launch_bounds__(256) f32_to_bf16_kernel(const float4* __restrict__ src, uint2* __restrict__ dst,
+                                                            long long n_vec4) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec4;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = ld_stream(src + i);
+    const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y);
+    const __nv_bfloat162 hi = __floats2bfloat162_rn(v.z, v.w);
+    uint2 o;
+    o.x = *reinterpret_cast<const unsigned*>(&lo);
+    o.y = *reinterpret_cast<const unsigned*>(&hi);
+    dst[i] = o;
   }
 }
 

@@ -170,12 +170,22 @@ std::vector<at::Tensor> ms_deform_attn_backward(const at::Tensor& value, const a
                         s.L, s.Lq, s.P, grad_value.data_ptr<double>(), grad_loc.data_ptr<double>(),
                         grad_aw.data_ptr<double>(), stream);
       break;
-    case Mode::BF16:
+    case Mode::BF16: {
+      // accurate mode by default: fp32 accumulation scratch, one rounding into the bf16 grad_value
+      int direct = 0;
+      msda_b200_get_option("bf16_direct_red", &direct);
+      at::Tensor scratch;
+      float* scratch_ptr = nullptr;
+      if (!direct) {
+        scratch = at::zeros(value.sizes(), value.options().dtype(at::kFloat));
+        scratch_ptr = scratch.data_ptr<float>();
+      }
       rc = msda_bwd_bf16(grad_output.data_ptr<float>(), reinterpret_cast<const uint16_t*>(value.data_ptr()),
                          shp, lsi, sampling_loc.data_ptr<float>(), attn_weight.data_ptr<float>(), s.N, s.S,
                          s.M, s.D, s.L, s.Lq, s.P, reinterpret_cast<uint16_t*>(grad_value.data_ptr()),
-                         grad_loc.data_ptr<float>(), grad_aw.data_ptr<float>(), stream);
+                         grad_loc.data_ptr<float>(), grad_aw.data_ptr<float>(), scratch_ptr, stream);
       break;
+    }
   }
   check_rc(rc, "ms_deform_attn_backward");
   return {grad_value, grad_loc, grad_aw};
