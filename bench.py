@@ -205,17 +205,12 @@ def main():
         return run_reference(args)
 
     import torch
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    from uvhand_b200 import sharding
+    world, rank, local_rank = sharding.env_world()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the operator has no CPU path (use --impl reference for the CPU port)")
     torch.cuda.set_device(local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dist = sharding.init_process_group("nccl", torch.device("cuda", local_rank))
     n_gpus = world if world > 1 else 1
 
     from uvhand_b200 import cabi
@@ -250,12 +245,9 @@ def main():
     total_ms = t0.elapsed_time(t1)
     fwd_ms = statistics.mean(e[0].elapsed_time(e[1]) for e in evs)
     bwd_ms = statistics.mean(e[1].elapsed_time(e[2]) for e in evs)
-    if dist is not None:
-        tt = torch.tensor([total_ms, fwd_ms, bwd_ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        total_ms, fwd_ms, bwd_ms = tt.tolist()
+    total_ms, fwd_ms, bwd_ms = sharding.max_over_ranks([total_ms, fwd_ms, bwd_ms], dist, "cuda")
     ms_per_step = total_ms / args.steps
-    value = n_gpus * wl.items / (ms_per_step * 1e-3)
+    value = sharding.aggregate_throughput(wl.items, n_gpus, ms_per_step * 1e-3)
 
     # ---- e2e: host buffers through the C ABI ------------------------------------------------
     e2e = None
@@ -284,11 +276,8 @@ def main():
             e2e_step()
         torch.cuda.synchronize()
         e2e_s = (time.perf_counter() - w0) / e2e_steps
-        if dist is not None:
-            tt = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            e2e_s = float(tt.item())
-        e2e = {"value": n_gpus * wl.items / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+        e2e_s = sharding.max_over_ranks([e2e_s], dist, "cuda")[0]
+        e2e = {"value": sharding.aggregate_throughput(wl.items, n_gpus, e2e_s), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
                "api": "msda_host_fwd_bwd_f32 (C ABI, pinned host buffers in and out)"}
         plan.close()
