@@ -21,8 +21,12 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--iters", type=int, default=40)
 ap.add_argument("--workloads", default="c2_detr_encoder:f32:encoder,c2_detr_encoder:f32:uniform,c2_detr_encoder:bf16:encoder,c3_arctic_encoder:f32:encoder,c4_dino_decoder:f32:twostage")
 ap.add_argument("--check", action="store_true")
+ap.add_argument("--opts", default="", help="library options, e.g. tile_l0=0x34,tile_mode=1")
 a = ap.parse_args()
-print("lib:", cabi.LIB_PATH)
+print("lib:", cabi.LIB_PATH, "opts:", a.opts)
+for kv in filter(None, a.opts.split(",")):
+    k, v = kv.split("=")
+    cabi.set_option(k, int(v, 0))
 st = torch.cuda.current_stream().cuda_stream
 
 ref = None

@@ -66,10 +66,14 @@ bool d32_eligible(int S, int M, int D, int L, int P) {
          (long long)S * M < kMaxTokenHeadsD32;
 }
 
-int d32_grid(long long n_items) {
+// CTAs per launch: enough for every warp pass, capped at `waves` x what the device holds at once
+// (resident CTAs per SM = the kernel's __launch_bounds__ minimum).  waves = 1 is a persistent grid
+// whose warps each run many passes (what the forward's software pipeline needs); a large cap gives
+// short-lived CTAs and lets the hardware scheduler balance the tail (better for the backward).
+int d32_grid(long long n_items, int resident_per_sm, int waves) {
   const long long n_pass = (n_items + kItemsPerWarp - 1) / kItemsPerWarp;
   long long ctas = (n_pass + kD32Warps - 1) / kD32Warps;
-  const long long cap = (long long)sm_count() * 64;
+  const long long cap = (long long)sm_count() * resident_per_sm * waves;
   if (ctas > cap) ctas = cap;
   if (ctas < 1) ctas = 1;
   return (int)ctas;
@@ -86,25 +90,27 @@ int generic_grid(long long n_items) {
 }
 
 template <typename VT>
-int launch_fwd_d32(const D32Params& p, cudaStream_t st) {
+int launch_fwd_d32(D32Params& p, cudaStream_t st) {
   const int LP = p.L * p.P;
-  const int grid = d32_grid(p.n_items);
-  if (p.L == 4 && p.P == 4) {
-    fwd_d32_kernel<VT, 4, 4><<<grid, kD32Threads, d32_smem(LP), st>>>(p);
+  p.n_items = (long long)p.N * p.Lq * p.M;
+  const int grid = d32_grid(p.n_items, MSDA_FWD_MINB, MSDA_FWD_WAVES);
+  if (p.L == 4 && p.P == 4 && p.M == 8) {   // the shipped geometry (util/settings.py:102-120)
+    fwd_d32_kernel<VT, 4, 4, 8><<<grid, kD32Threads, d32_smem(LP), st>>>(p);
   } else {
-    fwd_d32_kernel<VT, 0, 0><<<grid, kD32Threads, d32_smem(LP), st>>>(p);
+    fwd_d32_kernel<VT, 0, 0, 0><<<grid, kD32Threads, d32_smem(LP), st>>>(p);
   }
   return finish_launch(1);
 }
 
 template <typename VT, typename GT>
-int launch_bwd_d32(const D32Params& p, cudaStream_t st) {
+int launch_bwd_d32(D32Params& p, cudaStream_t st) {
   const int LP = p.L * p.P;
-  const int grid = d32_grid(p.n_items);
-  if (p.L == 4 && p.P == 4) {
-    bwd_d32_kernel<VT, GT, 4, 4><<<grid, kD32Threads, d32_smem(LP), st>>>(p);
+  p.n_items = (long long)p.N * p.Lq * p.M;
+  const int grid = d32_grid(p.n_items, MSDA_BWD_MINB, MSDA_BWD_WAVES);
+  if (p.L == 4 && p.P == 4 && p.M == 8) {
+    bwd_d32_kernel<VT, GT, 4, 4, 8><<<grid, kD32Threads, d32_smem(LP), st>>>(p);
   } else {
-    bwd_d32_kernel<VT, GT, 0, 0><<<grid, kD32Threads, d32_smem(LP), st>>>(p);
+    bwd_d32_kernel<VT, GT, 0, 0, 0><<<grid, kD32Threads, d32_smem(LP), st>>>(p);
   }
   return finish_launch(1);
 }
@@ -214,7 +220,6 @@ int msda_fwd_f32(const float* value, const int64_t* shapes, const int64_t* lsi, 
     D32Params p{};
     p.value = value; p.shapes = shapes; p.lsi = lsi; p.loc = loc; p.aw = aw; p.out = out;
     p.N = N; p.S = S; p.M = M; p.L = L; p.Lq = Lq; p.P = P;
-    p.n_items = (long long)N * Lq * M;
     g_last_path[0] = "fwd_d32_f32";
     return launch_fwd_d32<float>(p, st);
   }
@@ -262,7 +267,6 @@ int msda_fwd_bf16(const uint16_t* value, const int64_t* shapes, const int64_t* l
   D32Params p{};
   p.value = value; p.shapes = shapes; p.lsi = lsi; p.loc = loc; p.aw = aw; p.out = out;
   p.N = N; p.S = S; p.M = M; p.L = L; p.Lq = Lq; p.P = P;
-  p.n_items = (long long)N * Lq * M;
   g_last_path[0] = "fwd_d32_bf16";
   return launch_fwd_d32<__nv_bfloat16>(p, st);
 }
@@ -288,7 +292,6 @@ int msda_bwd_f32(const float* go, const float* value, const int64_t* shapes, con
     p.value = value; p.shapes = shapes; p.lsi = lsi; p.loc = loc; p.aw = aw; p.grad_out = go;
     p.grad_value = gv; p.grad_loc = gl; p.grad_aw = ga;
     p.N = N; p.S = S; p.M = M; p.L = L; p.Lq = Lq; p.P = P;
-    p.n_items = (long long)N * Lq * M;
     g_last_path[1] = "bwd_d32_f32";
     return launch_bwd_d32<float, float>(p, st);
   }
@@ -328,7 +331,6 @@ int msda_bwd_bf16(const float* go, const uint16_t* value, const int64_t* shapes,
   p.value = value; p.shapes = shapes; p.lsi = lsi; p.loc = loc; p.aw = aw; p.grad_out = go;
   p.grad_loc = gl; p.grad_aw = ga;
   p.N = N; p.S = S; p.M = M; p.L = L; p.Lq = Lq; p.P = P;
-  p.n_items = (long long)N * Lq * M;
   if (gv_scratch) {
     // accurate mode: fp32 reductions into the scratch, one rounding to bf16 at the end
     p.grad_value = gv_scratch;
@@ -371,7 +373,14 @@ struct msda_host_plan {
   size_t n_value, n_loc, n_aw, n_out;
   float *d_value, *d_loc, *d_aw, *d_go, *d_out, *d_gv, *d_gl, *d_ga;
   int64_t *d_shapes, *d_lsi;
-  cudaStream_t stream;
+  // Three streams so that upload, kernels and download overlap (PCIe is full duplex and the copy
+  // engines run beside the SMs): a call is cut into per-sample query chunks that flow through them.
+  cudaStream_t s_in, s_run, s_out;
+  int n_chunks;                 // query chunks per sample
+  cudaEvent_t* ev_in;           // [N * n_chunks] chunk inputs on the device
+  cudaEvent_t* ev_run;          // [N * n_chunks] chunk results computed
+  cudaEvent_t* ev_value;        // [N] value[b] on the device
+  cudaEvent_t ev_tables, ev_zero;
 };
 
 #define MSDA_CUDA_TRY(expr)                     \
@@ -401,7 +410,30 @@ int msda_host_plan_create(msda_host_plan** out_plan, int device, int N, int S, i
   pl->n_aw = (size_t)N * Lq * M * L * P;
   pl->n_loc = pl->n_aw * 2;
   pl->n_out = (size_t)N * Lq * M * D;
-  cudaError_t e = cudaStreamCreateWithFlags(&pl->stream, cudaStreamNonBlocking);
+  // chunks of about 16 MB of per-query traffic (in + out), at most 16 per sample
+  {
+    const double per_query = 4.0 * M * (2.0 * D + 6.0 * L * P);  // go + out + (loc, aw, gl, ga)
+    long long c = (long long)(per_query * Lq / (16.0 * 1024 * 1024) + 0.5);
+    if (c < 1) c = 1;
+    if (c > 16) c = 16;
+    if (c > Lq) c = Lq > 0 ? Lq : 1;
+    pl->n_chunks = (int)c;
+  }
+  cudaError_t e = cudaStreamCreateWithFlags(&pl->s_in, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&pl->s_run, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&pl->s_out, cudaStreamNonBlocking);
+  const int n_ev = (N > 0 ? N : 1) * pl->n_chunks;
+  pl->ev_in = new (std::nothrow) cudaEvent_t[n_ev]();
+  pl->ev_run = new (std::nothrow) cudaEvent_t[n_ev]();
+  pl->ev_value = new (std::nothrow) cudaEvent_t[N > 0 ? N : 1]();
+  if (!pl->ev_in || !pl->ev_run || !pl->ev_value) e = cudaErrorMemoryAllocation;
+  for (int i = 0; i < n_ev && e == cudaSuccess; ++i) {
+    e = cudaEventCreateWithFlags(&pl->ev_in[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&pl->ev_run[i], cudaEventDisableTiming);
+  }
+  for (int i = 0; i < N && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&pl->ev_value[i], cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&pl->ev_tables, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&pl->ev_zero, cudaEventDisableTiming);
   auto alloc = [&](float** p, size_t n) {
     if (e == cudaSuccess) e = cudaMalloc((void**)p, sizeof(float) * (n ? n : 1));
   };
@@ -429,7 +461,19 @@ void msda_host_plan_destroy(msda_host_plan* pl) {
   cudaFree(pl->d_value); cudaFree(pl->d_loc); cudaFree(pl->d_aw); cudaFree(pl->d_go);
   cudaFree(pl->d_out); cudaFree(pl->d_gv); cudaFree(pl->d_gl); cudaFree(pl->d_ga);
   cudaFree(pl->d_shapes); cudaFree(pl->d_lsi);
-  if (pl->stream) cudaStreamDestroy(pl->stream);
+  const int n_ev = (pl->N > 0 ? pl->N : 1) * pl->n_chunks;
+  for (int i = 0; i < n_ev; ++i) {
+    if (pl->ev_in && pl->ev_in[i]) cudaEventDestroy(pl->ev_in[i]);
+    if (pl->ev_run && pl->ev_run[i]) cudaEventDestroy(pl->ev_run[i]);
+  }
+  for (int i = 0; i < pl->N; ++i)
+    if (pl->ev_value && pl->ev_value[i]) cudaEventDestroy(pl->ev_value[i]);
+  delete[] pl->ev_in; delete[] pl->ev_run; delete[] pl->ev_value;
+  if (pl->ev_tables) cudaEventDestroy(pl->ev_tables);
+  if (pl->ev_zero) cudaEventDestroy(pl->ev_zero);
+  if (pl->s_in) cudaStreamDestroy(pl->s_in);
+  if (pl->s_run) cudaStreamDestroy(pl->s_run);
+  if (pl->s_out) cudaStreamDestroy(pl->s_out);
   delete pl;
 }
 
@@ -455,14 +499,69 @@ int msda_host_unregister(void* ptr) {
   return MSDA_OK;
 }
 
-static int host_upload(msda_host_plan* pl, const float* value, const int64_t* shapes,
-                       const int64_t* lsi, const float* loc, const float* aw) {
-  cudaStream_t st = pl->stream;
-  MSDA_CUDA_TRY(cudaMemcpyAsync(pl->d_shapes, shapes, sizeof(int64_t) * 2 * pl->L, cudaMemcpyHostToDevice, st));
-  MSDA_CUDA_TRY(cudaMemcpyAsync(pl->d_lsi, lsi, sizeof(int64_t) * pl->L, cudaMemcpyHostToDevice, st));
-  MSDA_CUDA_TRY(cudaMemcpyAsync(pl->d_value, value, sizeof(float) * pl->n_value, cudaMemcpyHostToDevice, st));
-  MSDA_CUDA_TRY(cudaMemcpyAsync(pl->d_loc, loc, sizeof(float) * pl->n_loc, cudaMemcpyHostToDevice, st));
-  MSDA_CUDA_TRY(cudaMemcpyAsync(pl->d_aw, aw, sizeof(float) * pl->n_aw, cudaMemcpyHostToDevice, st));
+// One call = N * n_chunks work packets (sample b, queries [q0, q1)):
+//   s_in : tables, then per sample: value[b], then per chunk: loc, aw (, grad_out)
+//   s_run: memset(grad_value); per chunk: forward (+ backward) on that query range of sample b
+//   s_out: per chunk: out (, grad_loc, grad_aw); after the last chunk of a sample: grad_value[b]
+// The kernels see each packet as a problem with batch 1 and q1-q0 queries (the operator has no
+// cross-query or cross-sample term), so nothing but pointer offsets is needed.
+static int host_pipeline(msda_host_plan* pl, const float* value, const int64_t* shapes, const int64_t* lsi,
+                         const float* loc, const float* aw, const float* go, float* out, float* gv,
+                         float* gl, float* ga) {
+  const bool bwd = go != nullptr;
+  const int N = pl->N, S = pl->S, M = pl->M, D = pl->D, L = pl->L, Lq = pl->Lq, P = pl->P;
+  if (N == 0) return MSDA_OK;
+  const size_t v_per = (size_t)S * M * D;
+  const size_t o_per_q = (size_t)M * D, a_per_q = (size_t)M * L * P;
+  const cudaMemcpyKind H2D = cudaMemcpyHostToDevice, D2H = cudaMemcpyDeviceToHost;
+  MSDA_CUDA_TRY(cudaMemcpyAsync(pl->d_shapes, shapes, sizeof(int64_t) * 2 * L, H2D, pl->s_in));
+  MSDA_CUDA_TRY(cudaMemcpyAsync(pl->d_lsi, lsi, sizeof(int64_t) * L, H2D, pl->s_in));
+  MSDA_CUDA_TRY(cudaEventRecord(pl->ev_tables, pl->s_in));
+  MSDA_CUDA_TRY(cudaStreamWaitEvent(pl->s_run, pl->ev_tables, 0));
+  if (bwd && pl->n_value) MSDA_CUDA_TRY(cudaMemsetAsync(pl->d_gv, 0, sizeof(float) * pl->n_value, pl->s_run));
+  for (int b = 0; b < N; ++b) {
+    if (v_per) MSDA_CUDA_TRY(cudaMemcpyAsync(pl->d_value + b * v_per, value + b * v_per, sizeof(float) * v_per, H2D, pl->s_in));
+    MSDA_CUDA_TRY(cudaEventRecord(pl->ev_value[b], pl->s_in));
+    MSDA_CUDA_TRY(cudaStreamWaitEvent(pl->s_run, pl->ev_value[b], 0));
+    for (int c = 0; c < pl->n_chunks; ++c) {
+      const int q0 = (int)((long long)Lq * c / pl->n_chunks), q1 = (int)((long long)Lq * (c + 1) / pl->n_chunks);
+      const int nq = q1 - q0;
+      const int k = b * pl->n_chunks + c;
+      const size_t qo = (size_t)b * Lq + q0;
+      if (nq > 0 && a_per_q) {
+        MSDA_CUDA_TRY(cudaMemcpyAsync(pl->d_loc + qo * a_per_q * 2, loc + qo * a_per_q * 2, sizeof(float) * nq * a_per_q * 2, H2D, pl->s_in));
+        MSDA_CUDA_TRY(cudaMemcpyAsync(pl->d_aw + qo * a_per_q, aw + qo * a_per_q, sizeof(float) * nq * a_per_q, H2D, pl->s_in));
+      }
+      if (bwd && nq > 0 && o_per_q)
+        MSDA_CUDA_TRY(cudaMemcpyAsync(pl->d_go + qo * o_per_q, go + qo * o_per_q, sizeof(float) * nq * o_per_q, H2D, pl->s_in));
+      MSDA_CUDA_TRY(cudaEventRecord(pl->ev_in[k], pl->s_in));
+      MSDA_CUDA_TRY(cudaStreamWaitEvent(pl->s_run, pl->ev_in[k], 0));
+      if (nq > 0) {
+        int rc = msda_fwd_f32(pl->d_value + b * v_per, pl->d_shapes, pl->d_lsi, pl->d_loc + qo * a_per_q * 2,
+                              pl->d_aw + qo * a_per_q, 1, S, M, D, L, nq, P, pl->d_out + qo * o_per_q, pl->s_run);
+        if (rc) return rc;
+        if (bwd) {
+          rc = msda_bwd_f32(pl->d_go + qo * o_per_q, pl->d_value + b * v_per, pl->d_shapes, pl->d_lsi,
+                            pl->d_loc + qo * a_per_q * 2, pl->d_aw + qo * a_per_q, 1, S, M, D, L, nq, P,
+                            pl->d_gv + b * v_per, pl->d_gl + qo * a_per_q * 2, pl->d_ga + qo * a_per_q, pl->s_run);
+          if (rc) return rc;
+        }
+      }
+      MSDA_CUDA_TRY(cudaEventRecord(pl->ev_run[k], pl->s_run));
+      MSDA_CUDA_TRY(cudaStreamWaitEvent(pl->s_out, pl->ev_run[k], 0));
+      if (nq > 0 && o_per_q)
+        MSDA_CUDA_TRY(cudaMemcpyAsync(out + qo * o_per_q, pl->d_out + qo * o_per_q, sizeof(float) * nq * o_per_q, D2H, pl->s_out));
+      if (bwd && nq > 0 && a_per_q) {
+        MSDA_CUDA_TRY(cudaMemcpyAsync(gl + qo * a_per_q * 2, pl->d_gl + qo * a_per_q * 2, sizeof(float) * nq * a_per_q * 2, D2H, pl->s_out));
+        MSDA_CUDA_TRY(cudaMemcpyAsync(ga + qo * a_per_q, pl->d_ga + qo * a_per_q, sizeof(float) * nq * a_per_q, D2H, pl->s_out));
+      }
+    }
+    if (bwd && v_per)
+      MSDA_CUDA_TRY(cudaMemcpyAsync(gv + b * v_per, pl->d_gv + b * v_per, sizeof(float) * v_per, D2H, pl->s_out));
+  }
+  MSDA_CUDA_TRY(cudaStreamSynchronize(pl->s_out));
+  MSDA_CUDA_TRY(cudaStreamSynchronize(pl->s_run));
+  MSDA_CUDA_TRY(cudaStreamSynchronize(pl->s_in));
   return MSDA_OK;
 }
 
@@ -470,14 +569,7 @@ int msda_host_fwd_f32(msda_host_plan* pl, const float* value, const int64_t* sha
                       const float* loc, const float* aw, float* out) {
   if (!pl || !value || !shapes || !lsi || !loc || !aw || !out) return MSDA_ERR_NULL_POINTER;
   MSDA_CUDA_TRY(cudaSetDevice(pl->device));
-  int rc = host_upload(pl, value, shapes, lsi, loc, aw);
-  if (rc) return rc;
-  rc = msda_fwd_f32(pl->d_value, pl->d_shapes, pl->d_lsi, pl->d_loc, pl->d_aw, pl->N, pl->S, pl->M,
-                    pl->D, pl->L, pl->Lq, pl->P, pl->d_out, pl->stream);
-  if (rc) return rc;
-  MSDA_CUDA_TRY(cudaMemcpyAsync(out, pl->d_out, sizeof(float) * pl->n_out, cudaMemcpyDeviceToHost, pl->stream));
-  MSDA_CUDA_TRY(cudaStreamSynchronize(pl->stream));
-  return MSDA_OK;
+  return host_pipeline(pl, value, shapes, lsi, loc, aw, nullptr, out, nullptr, nullptr, nullptr);
 }
 
 int msda_host_fwd_bwd_f32(msda_host_plan* pl, const float* value, const int64_t* shapes,
@@ -486,23 +578,7 @@ int msda_host_fwd_bwd_f32(msda_host_plan* pl, const float* value, const int64_t*
   if (!pl || !value || !shapes || !lsi || !loc || !aw || !go || !out || !gv || !gl || !ga)
     return MSDA_ERR_NULL_POINTER;
   MSDA_CUDA_TRY(cudaSetDevice(pl->device));
-  cudaStream_t st = pl->stream;
-  int rc = host_upload(pl, value, shapes, lsi, loc, aw);
-  if (rc) return rc;
-  rc = msda_fwd_f32(pl->d_value, pl->d_shapes, pl->d_lsi, pl->d_loc, pl->d_aw, pl->N, pl->S, pl->M,
-                    pl->D, pl->L, pl->Lq, pl->P, pl->d_out, st);
-  if (rc) return rc;
-  MSDA_CUDA_TRY(cudaMemcpyAsync(out, pl->d_out, sizeof(float) * pl->n_out, cudaMemcpyDeviceToHost, st));
-  MSDA_CUDA_TRY(cudaMemcpyAsync(pl->d_go, go, sizeof(float) * pl->n_out, cudaMemcpyHostToDevice, st));
-  MSDA_CUDA_TRY(cudaMemsetAsync(pl->d_gv, 0, sizeof(float) * pl->n_value, st));
-  rc = msda_bwd_f32(pl->d_go, pl->d_value, pl->d_shapes, pl->d_lsi, pl->d_loc, pl->d_aw, pl->N, pl->S,
-                    pl->M, pl->D, pl->L, pl->Lq, pl->P, pl->d_gv, pl->d_gl, pl->d_ga, st);
-  if (rc) return rc;
-  MSDA_CUDA_TRY(cudaMemcpyAsync(gv, pl->d_gv, sizeof(float) * pl->n_value, cudaMemcpyDeviceToHost, st));
-  MSDA_CUDA_TRY(cudaMemcpyAsync(gl, pl->d_gl, sizeof(float) * pl->n_loc, cudaMemcpyDeviceToHost, st));
-  MSDA_CUDA_TRY(cudaMemcpyAsync(ga, pl->d_ga, sizeof(float) * pl->n_aw, cudaMemcpyDeviceToHost, st));
-  MSDA_CUDA_TRY(cudaStreamSynchronize(st));
-  return MSDA_OK;
+  return host_pipeline(pl, value, shapes, lsi, loc, aw, go, out, gv, gl, ga);
 }
 
 }  // extern "C"

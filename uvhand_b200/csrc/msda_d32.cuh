@@ -41,6 +41,34 @@ namespace msda {
 #ifndef MSDA_BWD_MINB
 #define MSDA_BWD_MINB 4
 #endif
+// Tuning switches, defaults = what measured fastest on B200 at the DETR-encoder shape
+// (gpurun_out A/B logs summarised in profiles/r01_tuning_matrix.md):
+//   *_PREFETCH  software-pipelined phase A (next pass's locations/weights requested before the gathers)
+//   *_WAVES     grid cap in units of "CTAs the device holds at once": 1 = persistent grid
+//   FWD_PREDFMA forward corner loads and their FMAs share one predicate (no zero-fill of landing regs)
+//   BWD_PRED    same idea for the backward (load + dot + red under one predicate)
+//   STATIC_M    M = 8 compiled in: the x+1 corner becomes an immediate offset of the x corner's address
+#ifndef MSDA_FWD_PREFETCH
+#define MSDA_FWD_PREFETCH 1
+#endif
+#ifndef MSDA_BWD_PREFETCH
+#define MSDA_BWD_PREFETCH 0
+#endif
+#ifndef MSDA_FWD_WAVES
+#define MSDA_FWD_WAVES 1
+#endif
+#ifndef MSDA_BWD_WAVES
+#define MSDA_BWD_WAVES 11
+#endif
+#ifndef MSDA_FWD_PREDFMA
+#define MSDA_FWD_PREDFMA 1
+#endif
+#ifndef MSDA_BWD_PRED
+#define MSDA_BWD_PRED 0
+#endif
+#ifndef MSDA_STATIC_M
+#define MSDA_STATIC_M 1
+#endif
 
 constexpr int kD32Warps = 8;                  // warps per CTA
 constexpr int kD32Threads = kD32Warps * kWarp;
@@ -122,6 +150,42 @@ __device__ __forceinline__ void geometry_phase(int4* warp_recs, const D32Params&
   }
 }
 
+// Software-pipelined phase A (compile-time L*P with 4*L*P a multiple of 32): the raw locations
+// and weights of the NEXT pass are requested before the current pass starts gathering, so their
+// HBM latency (they are read exactly once, always cold) hides behind the gathers instead of
+// heading every pass.
+template <int kLP>
+struct RawSamples {
+  static constexpr int kPerLane = kItemsPerWarp * kLP / kWarp;
+  float2 xy[kPerLane];
+  float a[kPerLane];
+  __device__ __forceinline__ void load(const D32Params& p, long long item0, int lane) {
+    const long long s_base = item0 * kLP, s_end = p.n_items * kLP;
+#pragma unroll
+    for (int i = 0; i < kPerLane; ++i) {
+      const long long gs = s_base + lane + i * kWarp;
+      if (gs < s_end) {
+        xy[i] = ld_stream(reinterpret_cast<const float2*>(p.loc) + gs);
+        a[i] = ld_stream(p.aw + gs);
+      }
+    }
+  }
+  template <bool kBackward, int kP>
+  __device__ __forceinline__ void park(int4* warp_recs, const D32Params& p, const LevelTab& tab,
+                                       long long item0, int lane, int M) const {
+    const long long s_base = item0 * kLP, s_end = p.n_items * kLP;
+#pragma unroll
+    for (int i = 0; i < kPerLane; ++i) {
+      const int s = lane + i * kWarp;
+      if (s_base + s < s_end) {
+        const int grp = s / kLP, ls = s % kLP, l = ls / kP;
+        warp_recs[grp * rec_stride(kLP) + ls] =
+            make_record<kBackward>(xy[i].x, xy[i].y, a[i], tab.H[l], tab.W[l], tab.start[l], M);
+      }
+    }
+  }
+};
+
 __device__ __forceinline__ void fma4(float4& acc, float w, const float4& v) {
   acc.x = fmaf(w, v.x, acc.x);
   acc.y = fmaf(w, v.y, acc.y);
@@ -148,7 +212,7 @@ struct LevelStride {
 // ---------------------------------------------------------------------------------------------
 // Forward
 // ---------------------------------------------------------------------------------------------
-template <typename VT, int kL, int kP>  // compile-time levels / points (0,0: runtime)
+template <typename VT, int kL, int kP, int kM>  // compile-time levels / points / heads (0: runtime)
 __global__ void __launch_bounds__(kD32Threads, MSDA_FWD_MINB)
 fwd_d32_kernel(const D32Params p) {
   using C = Chunk<VT>;
@@ -165,15 +229,24 @@ fwd_d32_kernel(const D32Params p) {
   const int group = lane >> 3, sub = lane & 7;
   int4* warp_recs = reinterpret_cast<int4*>(smem_raw) + warp * (kItemsPerWarp * stride);
   const int4* my_recs = warp_recs + group * stride;
-  const int M = p.M;
+  const int M = (MSDA_STATIC_M && kM > 0) ? kM : p.M;   // compile-time M turns the x+1 corner into an immediate offset
   LevelStride<kL> lv;
   if (kStatic) lv.init(tab, M);
 
   const long long n_pass = (p.n_items + kItemsPerWarp - 1) / kItemsPerWarp;
   const long long pass_stride = (long long)gridDim.x * kD32Warps;
-  for (long long pass = (long long)blockIdx.x * kD32Warps + warp; pass < n_pass; pass += pass_stride) {
+  constexpr bool kPipe = kStatic && MSDA_FWD_PREFETCH && (kItemsPerWarp * kL * kP) % kWarp == 0;
+  RawSamples<kPipe ? kL * kP : kWarp> raw;
+  const long long pass0 = (long long)blockIdx.x * kD32Warps + warp;
+  if (kPipe && pass0 < n_pass) raw.load(p, pass0 * kItemsPerWarp, lane);
+  for (long long pass = pass0; pass < n_pass; pass += pass_stride) {
     const long long item0 = pass * kItemsPerWarp;
-    geometry_phase<false>(warp_recs, p, tab, item0, LP, lane);
+    if (kPipe) {
+      raw.template park<false, (kP > 0 ? kP : 1)>(warp_recs, p, tab, item0, lane, M);
+      if (pass + pass_stride < n_pass) raw.load(p, (pass + pass_stride) * kItemsPerWarp, lane);
+    } else {
+      geometry_phase<false>(warp_recs, p, tab, item0, LP, lane);
+    }
     __syncwarp();
 
     const long long item = item0 + group;
@@ -197,6 +270,14 @@ fwd_d32_kernel(const D32Params p) {
           const float w1 = ah - w2, w3 = al - w4;   // a*hh*(1-lw), a*lh*(1-lw)
           const Vec* r0 = vb + (long long)row * 8;
           const Vec* r1 = r0 + (long long)wm * 8;
+          // load and accumulate under ONE predicate per corner: no zero-fill of the landing
+          // registers, and an invalid corner is never read (zero padding = "do not load")
+#if MSDA_FWD_PREDFMA
+          if (r.x & 1) fma4(acc, w1, C::load(r0));
+          if (r.x & 2) fma4(acc, w2, C::load(r0 + M * 8));
+          if (r.x & 4) fma4(acc, w3, C::load(r1));
+          if (r.x & 8) fma4(acc, w4, C::load(r1 + M * 8));
+#else
           float4 v1 = make_float4(0.f, 0.f, 0.f, 0.f), v2 = v1, v3 = v1, v4 = v1;
           if (r.x & 1) v1 = C::load(r0);
           if (r.x & 2) v2 = C::load(r0 + M * 8);
@@ -206,6 +287,7 @@ fwd_d32_kernel(const D32Params p) {
           fma4(acc, w2, v2);
           fma4(acc, w3, v3);
           fma4(acc, w4, v4);
+#endif
         }
       }
       st_stream(reinterpret_cast<float4*>(p.out) + item * 8 + sub, acc);
@@ -252,18 +334,28 @@ __device__ __forceinline__ void bwd_sample(const int4 r, const typename Chunk<VT
   const float w1 = hh * hw, w2 = hh * lw, w3 = lh * hw, w4 = lh * lw;
   const long long o0 = (long long)row * 8, o1 = o0 + (long long)wm * 8;
   const int dx = M * 8;
-  float4 v1 = make_float4(0.f, 0.f, 0.f, 0.f), v2 = v1, v3 = v1, v4 = v1;
   const bool ok1 = live && (r.x & 1), ok2 = live && (r.x & 2), ok3 = live && (r.x & 4), ok4 = live && (r.x & 8);
+  const float4 t = scale4(a, g);  // top_grad * attn_weight (cuh:115)
+  // One predicate per corner guards its load, its dot product and its reduction: an invalid corner
+  // is never read, gets no atomic (cuh:119-151) and needs no zero-filled landing registers.
+#if MSDA_BWD_PRED
+  float d1 = 0.f, d2 = 0.f, d3 = 0.f, d4 = 0.f;
+  if (ok1) { d1 = dot4(g, C::load(vb + o0)); G::red_add(gvb + o0, scale4(w1, t)); }
+  if (ok2) { d2 = dot4(g, C::load(vb + o0 + dx)); G::red_add(gvb + o0 + dx, scale4(w2, t)); }
+  if (ok3) { d3 = dot4(g, C::load(vb + o1)); G::red_add(gvb + o1, scale4(w3, t)); }
+  if (ok4) { d4 = dot4(g, C::load(vb + o1 + dx)); G::red_add(gvb + o1 + dx, scale4(w4, t)); }
+#else
+  float4 v1 = make_float4(0.f, 0.f, 0.f, 0.f), v2 = v1, v3 = v1, v4 = v1;
   if (ok1) v1 = C::load(vb + o0);
   if (ok2) v2 = C::load(vb + o0 + dx);
   if (ok3) v3 = C::load(vb + o1);
   if (ok4) v4 = C::load(vb + o1 + dx);
-  const float4 t = scale4(a, g);  // top_grad * attn_weight (cuh:115)
   if (ok1) G::red_add(gvb + o0, scale4(w1, t));
   if (ok2) G::red_add(gvb + o0 + dx, scale4(w2, t));
   if (ok3) G::red_add(gvb + o1, scale4(w3, t));
   if (ok4) G::red_add(gvb + o1 + dx, scale4(w4, t));
   const float d1 = dot4(g, v1), d2 = dot4(g, v2), d3 = dot4(g, v3), d4 = dot4(g, v4);
+#endif
   pa = w1 * d1 + w2 * d2 + w3 * d3 + w4 * d4;                    // cuh:156
   px = (hh * (d2 - d1) + lh * (d4 - d3)) * a * Wf;               // cuh:157
   py = (hw * (d3 - d1) + lw * (d4 - d2)) * a * Hf;               // cuh:158
@@ -272,7 +364,7 @@ __device__ __forceinline__ void bwd_sample(const int4 r, const typename Chunk<VT
 // VT: storage type of value; GT: type grad_value is accumulated in (float: red.v4.f32 -- also used
 // for bf16 values accumulating into an fp32 scratch; __nv_bfloat16: red.v2.bf16x2 straight into a
 // bf16 grad_value, faster but every add rounds the running sum to 8 bits).
-template <typename VT, typename GT, int kL, int kP>
+template <typename VT, typename GT, int kL, int kP, int kM>
 __global__ void __launch_bounds__(kD32Threads, MSDA_BWD_MINB)
 bwd_d32_kernel(const D32Params p) {
   using C = Chunk<VT>;
@@ -290,13 +382,22 @@ bwd_d32_kernel(const D32Params p) {
   const int group = lane >> 3, sub = lane & 7;
   int4* warp_recs = reinterpret_cast<int4*>(smem_raw) + warp * (kItemsPerWarp * stride);
   const int4* my_recs = warp_recs + group * stride;
-  const int M = p.M;
+  const int M = (MSDA_STATIC_M && kM > 0) ? kM : p.M;   // compile-time M turns the x+1 corner into an immediate offset
 
   const long long n_pass = (p.n_items + kItemsPerWarp - 1) / kItemsPerWarp;
   const long long pass_stride = (long long)gridDim.x * kD32Warps;
-  for (long long pass = (long long)blockIdx.x * kD32Warps + warp; pass < n_pass; pass += pass_stride) {
+  constexpr bool kPipe = kStatic && MSDA_BWD_PREFETCH && (kItemsPerWarp * kL * kP) % kWarp == 0;
+  RawSamples<kPipe ? kL * kP : kWarp> raw;
+  const long long pass0 = (long long)blockIdx.x * kD32Warps + warp;
+  if (kPipe && pass0 < n_pass) raw.load(p, pass0 * kItemsPerWarp, lane);
+  for (long long pass = pass0; pass < n_pass; pass += pass_stride) {
     const long long item0 = pass * kItemsPerWarp;
-    geometry_phase<true>(warp_recs, p, tab, item0, LP, lane);
+    if (kPipe) {
+      raw.template park<true, (kP > 0 ? kP : 1)>(warp_recs, p, tab, item0, lane, M);
+      if (pass + pass_stride < n_pass) raw.load(p, (pass + pass_stride) * kItemsPerWarp, lane);
+    } else {
+      geometry_phase<true>(warp_recs, p, tab, item0, LP, lane);
+    }
     __syncwarp();
 
     // Groups past the end still take part in the shuffles (with zero data).
