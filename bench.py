@@ -391,6 +391,44 @@ def extended(torch, cabi, args):
     run("c5_hires_contended", "bf16", bf16_direct=True, tag="c5_hires_contended:bf16:contended:direct-bf16x2-red")
     run("c5_hires", "f32")
 
+    # softmax + location prologue, materialised by torch ops vs folded into the kernels
+    # (autograd forward + backward from the raw Linear outputs; what MSDeformAttn.forward does between its GEMMs)
+    from uvhand_b200.functions import MSDeformAttnFunction, MSDeformAttnFusedFunction
+    from uvhand_b200.workloads import encoder_reference_points
+    for name in ("c2_detr_encoder", "c3_arctic_encoder"):
+        wl = WORKLOADS[name]
+        N, S, M, D, L, Lq, P = wl.dims()
+        x = make_inputs(wl, seed=0, device="cuda")
+        ref = encoder_reference_points(wl.levels, "cuda")[None, :, None, :].expand(N, Lq, L, 2).contiguous()
+        leaves = {"value": x["value"], "off": torch.randn(N, Lq, M, L, P, 2, device="cuda") * 2.0,
+                  "logits": torch.randn(N, Lq, M, L * P, device="cuda")}
+        wh = torch.stack([x["shapes"][:, 1], x["shapes"][:, 0]], -1)
+
+        def unfused(v, off, lg):
+            w = torch.softmax(lg, -1).view(N, Lq, M, L, P)
+            loc = ref[:, :, None, :, None, :] + off / wh[None, None, None, :, None, :]
+            return MSDeformAttnFunction.apply(v, x["shapes"], x["lsi"], loc, w, 64)
+
+        def fused(v, off, lg):
+            return MSDeformAttnFusedFunction.apply(v, x["shapes"], x["lsi"], ref, off, lg)
+
+        for tag, fn in (("unfused", unfused), ("fused", fused)):
+            ts = []
+            for it in range(warmup + steps):
+                lv = {k: t.detach().requires_grad_(True) for k, t in leaves.items()}
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                out = fn(lv["value"], lv["off"], lv["logits"])
+                out.backward(x["grad_out"])
+                e1.record()
+                torch.cuda.synchronize()
+                if it >= warmup:
+                    ts.append(e0.elapsed_time(e1))
+            res[f"prologue_{tag}:{name}:fwd+bwd_from_raw_linear_outputs"] = {
+                "ms_per_step": statistics.median(ts), "items_per_s": wl.items / (statistics.median(ts) * 1e-3)}
+        del x, leaves
+        torch.cuda.empty_cache()
+
     # the reference's own kernels recompiled for sm_100a (informational; oracle/_ref is test infra)
     ref_so = os.path.join(ROOT, "oracle", "_ref", "libmsda_refcuda.so")
     if os.path.exists(ref_so):

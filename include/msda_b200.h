@@ -99,6 +99,33 @@ int msda_bwd_bf16(const float *grad_output, const uint16_t *value, const int64_t
                   uint16_t *grad_value, float *grad_sampling_loc, float *grad_attn_weight,
                   float *grad_value_scratch, void *stream);
 
+/* ---- fused prologue ----------------------------------------------------------------------
+ * The operator with the two elementwise steps that precede it in MSDeformAttn.forward folded in
+ * (models/ops/modules/ms_deform_attn.py:100-108):
+ *     attn_weight  = softmax(attn_logits over L*P)
+ *     sampling_loc = reference_points[:, :, None, :, None, :] + sampling_offsets / (W_l, H_l)
+ * so that locations and weights are never written to / re-read from HBM.
+ *   reference_points [N, Lq, L, 2]        (the 42-keypoint variant passes the keypoint centre)
+ *   sampling_offsets [N, Lq, M, L, P, 2]  raw output of the sampling_offsets Linear
+ *   attn_logits      [N, Lq, M, L*P]      raw output of the attention_weights Linear
+ * Location arithmetic is torch's operation for operation, so corner indices equal the unfused
+ * path's bit for bit.  channels must be 32, num_levels <= 8, num_levels*num_point <= 32
+ * (MSDA_ERR_UNSUPPORTED otherwise: callers then use the unfused entry points).
+ * Backward: grad_value accumulated (zero on entry); grad_sampling_offsets / grad_attn_logits fully
+ * written; grad_reference_points accumulated (zero on entry) or NULL when not wanted. */
+int msda_fused_fwd_f32(const float *value, const int64_t *spatial_shapes, const int64_t *level_start,
+                       const float *reference_points, const float *sampling_offsets,
+                       const float *attn_logits,
+                       int batch, int spatial_size, int num_heads, int channels, int num_levels,
+                       int num_query, int num_point, float *output, void *stream);
+int msda_fused_bwd_f32(const float *grad_output, const float *value, const int64_t *spatial_shapes,
+                       const int64_t *level_start, const float *reference_points,
+                       const float *sampling_offsets, const float *attn_logits,
+                       int batch, int spatial_size, int num_heads, int channels, int num_levels,
+                       int num_query, int num_point,
+                       float *grad_value, float *grad_sampling_offsets, float *grad_attn_logits,
+                       float *grad_reference_points, void *stream);
+
 /* ---- parity probe ----------------------------------------------------------------------
  * Dumps, for every (n, q, m, l, p), what the kernels' shared sample-geometry routine decides:
  * floor of the pixel coordinate and the corner mask (bit0..3 = corner v1..v4 inside the level,
@@ -137,7 +164,10 @@ int msda_host_fwd_bwd_f32(msda_host_plan *plan, const float *value, const int64_
 /* ---- tuning / introspection --------------------------------------------------------------
  * Keys: "fwd_path", "bwd_path": 0 = automatic, 1 = force the any-shape kernels (used by bench.py
  * and the tests to exercise every kernel on the same inputs); "bf16_direct_red": 0/1, read by the
- * torch host layer to pick msda_bwd_bf16's accumulation mode (0 = fp32 scratch, the default).
+ * torch host layer to pick msda_bwd_bf16's accumulation mode (0 = fp32 scratch, the default);
+ * "split_mode": which D=32 kernels serve a call: 0 = by problem size (small calls such as 300/900
+ * decoder queries use the one-item-per-warp kernels, large ones four items per warp), 1 = never
+ * split, 2 = always split.  None of these changes results beyond summation order.
  * Returns MSDA_OK or MSDA_ERR_BAD_OPTION. */
 int msda_b200_set_option(const char *key, int value);
 int msda_b200_get_option(const char *key, int *value);

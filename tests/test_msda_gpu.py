@@ -40,18 +40,26 @@ def dev(a, dtype=None):
 
 
 class Paths:
-    """Context manager forcing a kernel family: 0 auto, 1 any-shape kernels."""
+    """Context manager forcing a kernel family.  fwd/bwd: 0 auto, 1 any-shape kernels;
+    split: 0 auto (by problem size), 1 never (4 items per warp), 2 always (1 item per warp)."""
 
-    def __init__(self, fwd=0, bwd=0):
-        self.f, self.b = fwd, bwd
+    def __init__(self, fwd=0, bwd=0, split=0):
+        self.f, self.b, self.s = fwd, bwd, split
 
     def __enter__(self):
         cabi.set_option("fwd_path", self.f)
         cabi.set_option("bwd_path", self.b)
+        cabi.set_option("split_mode", self.s)
 
     def __exit__(self, *a):
         cabi.set_option("fwd_path", 0)
         cabi.set_option("bwd_path", 0)
+        cabi.set_option("split_mode", 0)
+
+
+# the three kernel families every parity case runs through (D = 32 shapes)
+FAMILIES = {"d32": (0, 0, 1), "split": (0, 0, 2), "anyshape": (1, 1, 0)}
+FAMILY_IDS = list(FAMILIES)
 
 
 def run_cabi(kind, value, shapes, lsi, loc, aw, grad_out=None, bf16_direct=False):
@@ -109,15 +117,17 @@ def np_inputs(wl, seed, **kw):
 # golden vectors written by the unmodified reference (fp64 grid_sample path + autograd)
 # ------------------------------------------------------------------------------------------------
 
-@pytest.mark.parametrize("forced", [0, 1], ids=["auto", "anyshape"])
+@pytest.mark.parametrize("forced", FAMILY_IDS)
 @pytest.mark.parametrize("path", GOLDEN, ids=IDS)
 def test_golden_f32(path, forced):
     g = np.load(path)
-    with Paths(forced, forced):
+    with Paths(*FAMILIES[forced]):
         res = run_cabi("f32", g["value"], g["shapes"], g["lsi"], g["loc"], g["aw"], g["grad_out"])
     check_all(res, g)
-    if forced == 0 and g["value"].shape[3] == 32:
-        assert res["fwd_path"] == "fwd_d32_f32" and res["bwd_path"] == "bwd_d32_f32"
+    if g["value"].shape[3] == 32:
+        want = {"d32": ("fwd_d32_f32", "bwd_d32_f32"), "split": ("fwd_d32_split_f32", "bwd_d32_split_f32"),
+                "anyshape": ("fwd_generic_f32", "bwd_generic_f32")}[forced]
+        assert (res["fwd_path"], res["bwd_path"]) == want
 
 
 @pytest.mark.parametrize("path", GOLDEN, ids=IDS)
@@ -186,13 +196,13 @@ def test_sample_index_bit_exact(levels):
         assert np.array_equal(w, w0)
 
 
-@pytest.mark.parametrize("forced", [0, 1], ids=["auto", "anyshape"])
+@pytest.mark.parametrize("forced", FAMILY_IDS)
 def test_grad_value_touch_pattern_exact(forced):
     """Which value rows receive gradient is pure index/mask work: the set must match exactly."""
     wl = Workload("t", 2, ((9, 13), (5, 7), (3, 4), (2, 2)), 60, loc_dist="twostage")
     x = np_inputs(wl, 7, pad_frac=0.0)
     x["grad_out"] = np.ones_like(x["grad_out"])
-    with Paths(forced, forced):
+    with Paths(*FAMILIES[forced]):
         res = run_cabi("f32", x["value"], x["shapes"], x["lsi"], x["loc"], x["aw"], x["grad_out"])
     ref = oracle(x["value"], x["shapes"], x["lsi"], x["loc"], x["aw"], x["grad_out"])
     assert np.array_equal(res["grad_value"] != 0, ref["grad_value"] != 0)
@@ -210,26 +220,28 @@ MID_LEVELS = ((40, 57), (20, 29), (10, 15), (5, 8))
 MID_S = sum(h * w for h, w in MID_LEVELS)
 
 
-@pytest.mark.parametrize("forced", [0, 1], ids=["auto", "anyshape"])
+@pytest.mark.parametrize("forced", FAMILY_IDS)
 @pytest.mark.parametrize("dist,Lq", [("encoder", MID_S), ("uniform", 777), ("twostage", 300), ("contended", 512)])
 def test_mid_size_f32(dist, Lq, forced):
     wl = Workload("mid", 2, MID_LEVELS, Lq, loc_dist=dist)
     x = np_inputs(wl, 3)
-    with Paths(forced, forced):
+    with Paths(*FAMILIES[forced]):
         res = run_cabi("f32", x["value"], x["shapes"], x["lsi"], x["loc"], x["aw"], x["grad_out"])
     check_all(res, oracle(x["value"], x["shapes"], x["lsi"], x["loc"], x["aw"], x["grad_out"]))
 
 
+@pytest.mark.parametrize("split", [1, 2], ids=["d32", "split"])
 @pytest.mark.parametrize("direct", [False, True], ids=["f32acc", "direct-bf16x2"])
 @pytest.mark.parametrize("dist,Lq", [("encoder", MID_S), ("twostage", 300)])
-def test_mid_size_bf16(dist, Lq, direct):
+def test_mid_size_bf16(dist, Lq, direct, split):
     wl = Workload("mid", 2, MID_LEVELS, Lq, loc_dist=dist)
     x = np_inputs(wl, 4)
     v_bf16 = torch.from_numpy(x["value"]).to(torch.bfloat16)
     v_round = v_bf16.float().numpy()                      # what the kernel actually reads
-    res = run_cabi("bf16", v_round, x["shapes"], x["lsi"], x["loc"], x["aw"], x["grad_out"], bf16_direct=direct)
+    with Paths(0, 0, split):
+        res = run_cabi("bf16", v_round, x["shapes"], x["lsi"], x["loc"], x["aw"], x["grad_out"], bf16_direct=direct)
     ref = oracle(v_round, x["shapes"], x["lsi"], x["loc"], x["aw"], x["grad_out"])
-    assert res["fwd_path"] == "fwd_d32_bf16"
+    assert res["fwd_path"] == ("fwd_d32_bf16" if split == 1 else "fwd_d32_split_bf16")
     assert res["bwd_path"] == ("bwd_d32_bf16" if direct else "bwd_d32_bf16_f32acc")
     close(res["out"], ref["out"], FWD_RTOL)               # same rounded inputs -> fp32-level agreement
     close(res["grad_loc"], ref["grad_loc"], GRAD_RTOL)
@@ -270,13 +282,16 @@ SHAPES = [
 
 
 @pytest.mark.parametrize("shape", SHAPES, ids=[f"N{s[0]}M{s[1]}D{s[2]}L{s[3]}P{s[4]}Lq{s[5]}" for s in SHAPES])
-@pytest.mark.parametrize("kind", ["f32", "f64"])
+@pytest.mark.parametrize("kind", ["f32", "f32-split", "f64"])
 def test_shape_sweep(shape, kind):
     N, M, D, L, P, Lq, levels = shape
     wl = Workload("s", N, levels, Lq, M=M, D=D, P=P, loc_dist="twostage")
     x = np_inputs(wl, 9, pad_frac=0.0, offset_px=1.0)
     x["loc"] = (x["loc"] * 0.4 + 0.5).astype(np.float32)   # mostly inside, some out
-    res = run_cabi(kind, x["value"], x["shapes"], x["lsi"], x["loc"], x["aw"], x["grad_out"])
+    split = 2 if kind == "f32-split" else 1                # 4-items-per-warp vs 1-item-per-warp kernels
+    kind = kind.split("-")[0]
+    with Paths(0, 0, split):
+        res = run_cabi(kind, x["value"], x["shapes"], x["lsi"], x["loc"], x["aw"], x["grad_out"])
     variant = "f32x" if kind == "f32" else "f64"
     ref = oracle(x["value"], x["shapes"], x["lsi"], x["loc"], x["aw"], x["grad_out"], variant)
     if kind == "f32":
@@ -293,8 +308,8 @@ def test_special_locations_contribute_zero():
     loc[0, 1, :, 1, 1] = [0.5, np.inf]
     loc[0, 2, :, 0, 2] = [-np.inf, np.nan]
     loc[0, 3, :, 1, 3] = [7.0, 0.5]
-    for forced in (0, 1):
-        with Paths(forced, forced):
+    for forced in FAMILY_IDS:
+        with Paths(*FAMILIES[forced]):
             res = run_cabi("f32", x["value"], x["shapes"], x["lsi"], loc, x["aw"], x["grad_out"])
         ref = oracle(x["value"], x["shapes"], x["lsi"], loc, x["aw"], x["grad_out"])
         for k in ("out", "grad_value", "grad_loc", "grad_aw"):
@@ -312,8 +327,8 @@ def test_invalid_corners_are_never_read():
     # all samples in the top-left pixel's upper-left quadrant: h_low = w_low = -1, only corner v4 = (0,0) valid
     x["loc"][...] = np.float32(0.05)
     x["value"][0, 1:] = np.inf                      # every row except pixel (0,0)
-    for forced in (0, 1):
-        with Paths(forced, forced):
+    for forced in FAMILY_IDS:
+        with Paths(*FAMILIES[forced]):
             res = run_cabi("f32", x["value"], x["shapes"], x["lsi"], x["loc"], x["aw"], x["grad_out"])
         assert np.isfinite(res["out"]).all()
         assert np.isfinite(res["grad_loc"]).all() and np.isfinite(res["grad_aw"]).all()
@@ -347,7 +362,9 @@ def _full_size(wl, kind="f32", seed=0):
 def test_full_size_properties_f32(name):
     wl = WORKLOADS[name]
     t, out, gv, gl, ga = _full_size(wl)
-    assert cabi.last_path(False) == "fwd_d32_f32" and cabi.last_path(True) == "bwd_d32_f32"
+    # the 900/1098-query decoders are small enough for the one-item-per-warp kernels
+    want = ("fwd_d32_split_f32" if name.startswith("c4") else "fwd_d32_f32", "bwd_d32_f32")
+    assert (cabi.last_path(False), cabi.last_path(True)) == want
     g = t["grad_out"].view_as(out).double()
     # forward is linear in value and in the weights: <out, g> = <value, grad_value> = <w, grad_w>
     lhs = float((out.double() * g).sum())
@@ -450,11 +467,11 @@ def test_function_dtype_policy():
     vb = x["value"].bfloat16().requires_grad_(True)
     assert not F.get_bf16_value_mode()
     out_b = MSDeformAttnFunction.apply(vb, *args)
-    assert cabi.last_path(False) == "fwd_d32_f32"
+    assert cabi.last_path(False) in ("fwd_d32_f32", "fwd_d32_split_f32")
     F.set_bf16_value_mode(True)
     try:
         out_n = MSDeformAttnFunction.apply(vb, *args)
-        assert cabi.last_path(False) == "fwd_d32_bf16"
+        assert cabi.last_path(False) in ("fwd_d32_bf16", "fwd_d32_split_bf16")
         assert torch.allclose(out_n, out_b, rtol=1e-5, atol=1e-5)
         out_n.backward(x["grad_out"])
         assert vb.grad.dtype == torch.bfloat16 and cabi.last_path(True) == "bwd_d32_bf16_f32acc"
@@ -549,6 +566,164 @@ def test_module_against_grid_sample_port(ref_dim):
     assert torch.allclose(out, out2, rtol=1e-4, atol=1e-5)
     assert torch.allclose(gq, query.grad, rtol=1e-3, atol=1e-5)
     assert torch.allclose(gf, feat.grad, rtol=1e-3, atol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------------
+# fused prologue: softmax + reference/offset arithmetic inside the kernels
+# ------------------------------------------------------------------------------------------------
+
+def _fused_inputs(N, M, L, P, Lq, levels, seed, ref_spread=1.0):
+    """Raw module-side operands: reference points, pixel offsets, logits (+ value, grad_out)."""
+    rng = np.random.default_rng(seed)
+    S = sum(h * w for h, w in levels)
+    shapes = np.asarray(levels, np.int64).reshape(-1, 2)
+    lsi = np.concatenate([[0], np.cumsum(shapes.prod(1))[:-1]]).astype(np.int64)
+    value = rng.standard_normal((N, S, M, 32)).astype(np.float32)
+    ref = (0.5 + ref_spread * (rng.random((N, Lq, L, 2)) - 0.5)).astype(np.float32)
+    off = (rng.standard_normal((N, Lq, M, L, P, 2)) * 2.0).astype(np.float32)
+    logits = rng.standard_normal((N, Lq, M, L * P)).astype(np.float32)
+    go = rng.standard_normal((N, Lq, M * 32)).astype(np.float32)
+    return dict(value=value, shapes=shapes, lsi=lsi, ref=ref, off=off, logits=logits, grad_out=go)
+
+
+def _fused_reference(x):
+    """Unfused restatement: torch's fp32 location arithmetic in numpy fp32 (division then addition,
+    each correctly rounded), softmax in fp64, then the C oracle and the chain rule by hand."""
+    shapes = x["shapes"]
+    wh = np.stack([shapes[:, 1], shapes[:, 0]], -1).astype(np.float32)            # (W, H) per level
+    loc = (x["ref"][:, :, None, :, None, :] + x["off"] / wh[None, None, None, :, None, :]).astype(np.float32)
+    lg = x["logits"].astype(np.float64)
+    e = np.exp(lg - lg.max(-1, keepdims=True))
+    a64 = e / e.sum(-1, keepdims=True)
+    N, Lq, M, L, P, _ = x["off"].shape
+    a = a64.astype(np.float32).reshape(N, Lq, M, L, P)
+    out = c_oracle.forward(x["value"], shapes, x["lsi"], loc, a, "f32x")
+    gv, gl, ga = c_oracle.backward(x["grad_out"], x["value"], shapes, x["lsi"], loc, a, "f32x")
+    g_off = gl / wh[None, None, None, :, None, :].astype(np.float64)
+    ga_f = ga.reshape(N, Lq, M, L * P)
+    g_logits = a64 * (ga_f - (a64 * ga_f).sum(-1, keepdims=True))
+    g_ref = gl.sum(axis=(2, 4))
+    return loc, a, dict(out=out, grad_value=gv, grad_off=g_off, grad_logits=g_logits, grad_ref=g_ref)
+
+
+def _run_fused(x, want_ref=True):
+    t = {k: dev(v) for k, v in x.items()}
+    N, S, M, D = t["value"].shape
+    _, Lq, _, L, P, _ = t["off"].shape
+    dims = (N, S, M, D, L, Lq, P)
+    st = torch.cuda.current_stream().cuda_stream
+    out = torch.full((N, Lq, M * D), float("nan"), device="cuda")
+    cabi.fused_forward(t["value"].data_ptr(), t["shapes"].data_ptr(), t["lsi"].data_ptr(), t["ref"].data_ptr(),
+                       t["off"].data_ptr(), t["logits"].data_ptr(), dims, out.data_ptr(), st)
+    fwd_path = cabi.last_path(False)
+    gv = torch.zeros_like(t["value"])
+    goff = torch.full_like(t["off"], float("nan"))
+    glog = torch.full_like(t["logits"], float("nan"))
+    gref = torch.zeros_like(t["ref"]) if want_ref else None
+    cabi.fused_backward(t["grad_out"].data_ptr(), t["value"].data_ptr(), t["shapes"].data_ptr(), t["lsi"].data_ptr(),
+                        t["ref"].data_ptr(), t["off"].data_ptr(), t["logits"].data_ptr(), dims, gv.data_ptr(),
+                        goff.data_ptr(), glog.data_ptr(), gref.data_ptr() if want_ref else None, st)
+    torch.cuda.synchronize()
+    return dict(out=out.cpu().numpy(), grad_value=gv.cpu().numpy(), grad_off=goff.cpu().numpy(),
+                grad_logits=glog.cpu().numpy(), grad_ref=gref.cpu().numpy() if want_ref else None,
+                fwd_path=fwd_path, bwd_path=cabi.last_path(True)), t
+
+
+FUSED_CASES = [
+    # (N, M, L, P, Lq, levels, split)                                    what it exercises
+    (2, 8, 4, 4, 611, ((20, 27), (10, 14), (5, 7), (3, 4)), 1),      # shipped geometry: shuffle softmax, pipelined phase A
+    (2, 8, 4, 4, 77, ((20, 27), (10, 14), (5, 7), (3, 4)), 2),       # one-item-per-warp forward
+    (1, 3, 3, 2, 50, ((9, 7), (5, 4), (2, 2)), 1),                   # L*P = 6, M % 4 != 0: looped softmax
+    (1, 2, 8, 4, 21, tuple((4, 3) for _ in range(8)), 1),            # L*P = 32
+    (1, 2, 8, 4, 21, tuple((4, 3) for _ in range(8)), 2),
+    (2, 8, 2, 4, 33, ((6, 5), (3, 3)), 1),                           # L*P = 8 (power of two, runtime path)
+]
+
+
+@pytest.mark.parametrize("case", FUSED_CASES, ids=[f"N{c[0]}M{c[1]}L{c[2]}P{c[3]}Lq{c[4]}s{c[6]}" for c in FUSED_CASES])
+def test_fused_prologue_matches_unfused_restatement(case):
+    N, M, L, P, Lq, levels, split = case
+    x = _fused_inputs(N, M, L, P, Lq, levels, seed=17, ref_spread=1.3)     # some references outside [0, 1]
+    loc, a, ref = _fused_reference(x)
+    with Paths(0, 0, split):
+        res, t = _run_fused(x)
+        assert "fused" in res["fwd_path"] and ("split" in res["fwd_path"]) == (split == 2)
+        assert res["bwd_path"] == "bwd_d32_fused_f32"
+        # same locations bit for bit => the unfused kernels fed torch's own loc / softmax agree to rounding
+        unf = run_cabi("f32", x["value"], x["shapes"], x["lsi"], loc, a, x["grad_out"])
+    close(res["out"], ref["out"], FWD_RTOL)
+    close(res["out"], unf["out"], 2e-6)
+    close(res["grad_value"], ref["grad_value"], GRAD_RTOL)
+    close(res["grad_off"], ref["grad_off"], GRAD_RTOL)
+    close(res["grad_logits"], ref["grad_logits"], GRAD_RTOL)
+    close(res["grad_ref"], ref["grad_ref"], GRAD_RTOL)
+    # indices: which value rows receive gradient is integer work and must match the unfused path exactly
+    assert np.array_equal(res["grad_value"] != 0, unf["grad_value"] != 0)
+    res2, _ = _run_fused(x, want_ref=False)
+    assert np.array_equal(res2["grad_off"], res["grad_off"]) and res2["grad_ref"] is None
+
+
+def test_fused_locations_are_torch_bits():
+    """The fused kernels must land on exactly the pixels torch's `ref + off / wh` lands on, including
+    at exact pixel centres where a 1-ulp difference flips the floor."""
+    levels = ((100, 167), (50, 84), (25, 42), (13, 21))
+    wl = Workload("f", 1, levels, sum(h * w for h, w in levels))
+    shapes, lsi = (t.cuda() for t in __import__("uvhand_b200.workloads", fromlist=["level_tensors"]).level_tensors(levels))
+    from uvhand_b200.workloads import encoder_reference_points
+    ref = encoder_reference_points(levels, "cuda")[None, :, None, :].expand(1, wl.Lq, 4, 2).contiguous()
+    # whole-pixel offsets (the module's initial ring, ms_deform_attn.py:62-70): samples sit ON pixel centres
+    off = torch.randint(-3, 4, (1, wl.Lq, 8, 4, 4, 2), device="cuda").float()
+    wh = torch.stack([shapes[:, 1], shapes[:, 0]], -1).float()
+    loc = (ref[:, :, None, :, None, :] + off / wh[None, None, None, :, None, :]).contiguous()
+    value = torch.randn(1, wl.S, 8, 32, device="cuda")
+    logits = torch.zeros(1, wl.Lq, 8, 16, device="cuda")
+    aw = torch.full((1, wl.Lq, 8, 4, 4), 1.0 / 16, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    out_f = torch.empty(1, wl.Lq, 256, device="cuda")
+    out_u = torch.empty_like(out_f)
+    cabi.fused_forward(value.data_ptr(), shapes.data_ptr(), lsi.data_ptr(), ref.data_ptr(), off.data_ptr(),
+                       logits.data_ptr(), wl.dims(), out_f.data_ptr(), st)
+    cabi.forward("f32", value.data_ptr(), shapes.data_ptr(), lsi.data_ptr(), loc.data_ptr(), aw.data_ptr(), wl.dims(),
+                 out_u.data_ptr(), st)
+    torch.cuda.synchronize()
+    assert torch.equal(out_f, out_u)          # uniform weights are exact (1/16): any difference is an index difference
+
+
+@pytest.mark.parametrize("ref_dim", [2, 42])
+def test_module_fused_prologue_equals_unfused(ref_dim):
+    from uvhand_b200.modules import MSDeformAttn
+    torch.manual_seed(11)
+    levels = ((12, 17), (6, 9), (3, 5), (2, 3))
+    shapes = torch.as_tensor(levels, dtype=torch.long).cuda()
+    lsi = torch.cat((shapes.new_zeros((1,)), shapes.prod(1).cumsum(0)[:-1]))
+    S = int(shapes.prod(1).sum())
+    N, Lq = 2, 41
+    plain = MSDeformAttn(256, 4, 8, 4).cuda()
+    with torch.no_grad():
+        plain.sampling_offsets.weight.normal_(0, 0.02)
+        plain.attention_weights.weight.normal_(0, 0.1)
+    fused = MSDeformAttn(256, 4, 8, 4, fuse_prologue=True).cuda()
+    fused.load_state_dict(plain.state_dict())
+    pad = torch.zeros(N, S, dtype=torch.bool, device="cuda")
+    pad[:, -7:] = True
+    base = dict(query=torch.randn(N, Lq, 256, device="cuda"), feat=torch.randn(N, S, 256, device="cuda"),
+                refp=torch.rand(N, Lq, 4, ref_dim, device="cuda"))
+    outs = []
+    for mod in (plain, fused):
+        leaf = {k: v.clone().requires_grad_(True) for k, v in base.items()}
+        n0 = cabi.launch_count()
+        out = mod(leaf["query"], leaf["refp"], leaf["feat"], shapes, lsi, pad)
+        out.square().sum().backward()
+        torch.cuda.synchronize()
+        assert cabi.launch_count() - n0 == 2
+        assert ("fused" in cabi.last_path(False)) == mod.fuse_prologue
+        outs.append((out.detach(), {k: v.grad for k, v in leaf.items()}, {k: p.grad for k, p in mod.named_parameters()}))
+    (o0, g0, p0), (o1, g1, p1) = outs
+    assert torch.allclose(o0, o1, rtol=1e-5, atol=1e-6)
+    for k in g0:
+        assert torch.allclose(g0[k], g1[k], rtol=1e-4, atol=1e-4 * float(g0[k].abs().max())), k
+    for k in p0:
+        assert torch.allclose(p0[k], p1[k], rtol=1e-4, atol=1e-4 * float(p0[k].abs().max())), k
 
 
 # ------------------------------------------------------------------------------------------------

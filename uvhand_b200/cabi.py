@@ -20,6 +20,7 @@ SYMBOLS = (
     "msda_b200_abi_version", "msda_b200_strerror", "msda_b200_check_im2col_step",
     "msda_fwd_f32", "msda_fwd_f64", "msda_fwd_bf16",
     "msda_bwd_f32", "msda_bwd_f64", "msda_bwd_bf16",
+    "msda_fused_fwd_f32", "msda_fused_bwd_f32",
     "msda_sample_index_f32",
     "msda_host_plan_create", "msda_host_plan_destroy", "msda_host_plan_traffic",
     "msda_host_register", "msda_host_unregister", "msda_host_fwd_f32", "msda_host_fwd_bwd_f32",
@@ -55,6 +56,8 @@ def lib() -> ctypes.CDLL:
         for name in ("msda_bwd_f32", "msda_bwd_f64"):
             getattr(L, name).argtypes = [c_void_p] * 6 + seven + [c_void_p] * 4
         L.msda_bwd_bf16.argtypes = [c_void_p] * 6 + seven + [c_void_p] * 5
+        L.msda_fused_fwd_f32.argtypes = [c_void_p] * 6 + seven + [c_void_p, c_void_p]
+        L.msda_fused_bwd_f32.argtypes = [c_void_p] * 7 + seven + [c_void_p] * 5
         L.msda_sample_index_f32.argtypes = [c_void_p, c_void_p] + [c_int] * 5 + [c_void_p] * 4
         L.msda_host_plan_create.argtypes = [ctypes.POINTER(c_void_p), c_int] + seven
         L.msda_host_plan_destroy.argtypes = [c_void_p]
@@ -115,6 +118,19 @@ def backward(kind: str, go_ptr, value_ptr, shapes_ptr, lsi_ptr, loc_ptr, aw_ptr,
     else:
         rc = fn(go_ptr, value_ptr, shapes_ptr, lsi_ptr, loc_ptr, aw_ptr, *dims, gv_ptr, gl_ptr, ga_ptr, stream)
     check(rc, "msda_bwd_" + kind)
+
+
+def fused_forward(value_ptr, shapes_ptr, lsi_ptr, ref_ptr, offsets_ptr, logits_ptr, dims, out_ptr, stream=0) -> None:
+    """msda_fused_fwd_f32: softmax + location prologue folded into the operator (fp32, D = 32)."""
+    check(lib().msda_fused_fwd_f32(value_ptr, shapes_ptr, lsi_ptr, ref_ptr, offsets_ptr, logits_ptr, *dims, out_ptr,
+                                   stream), "msda_fused_fwd_f32")
+
+
+def fused_backward(go_ptr, value_ptr, shapes_ptr, lsi_ptr, ref_ptr, offsets_ptr, logits_ptr, dims,
+                   gv_ptr, goff_ptr, glogit_ptr, gref_ptr=None, stream=0) -> None:
+    """msda_fused_bwd_f32; gv (and gref when given) must be zero on entry."""
+    check(lib().msda_fused_bwd_f32(go_ptr, value_ptr, shapes_ptr, lsi_ptr, ref_ptr, offsets_ptr, logits_ptr, *dims,
+                                   gv_ptr, goff_ptr, glogit_ptr, gref_ptr, stream), "msda_fused_bwd_f32")
 
 
 def sample_index(shapes_ptr, loc_ptr, N, Lq, M, L, P, h_ptr, w_ptr, mask_ptr, stream=0) -> None:

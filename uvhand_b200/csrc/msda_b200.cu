@@ -22,6 +22,7 @@ using namespace msda;
 std::atomic<int> g_fwd_path{0};
 std::atomic<int> g_bwd_path{0};
 std::atomic<int> g_bf16_direct{0};
+std::atomic<int> g_split_mode{0};   // 0 auto, 1 never, 2 always
 std::atomic<long long> g_launches{0};
 const char* g_last_path[2] = {"none", "none"};
 
@@ -89,28 +90,63 @@ int generic_grid(long long n_items) {
   return (int)ctas;
 }
 
-template <typename VT>
-int launch_fwd_d32(D32Params& p, cudaStream_t st) {
+// Small forward calls run the split kernel (one item per warp): when the 4-items-per-warp
+// decomposition would leave the device with less than about one wave of warps, the call costs the
+// latency of each warp's sample chain, not bandwidth (900-query DINO decoder: 24.5 -> 18.5 us).
+// The backward does not gain (its chain is dominated by fire-and-forget reductions: 22.7 -> 26.6 us
+// when split), so it only splits on request.  Measured in profiles/r01_tuning_matrix.md.
+bool use_split(long long n_items, int resident_per_sm, bool backward) {
+  const int mode = g_split_mode.load();
+  if (mode == 1) return false;
+  if (mode == 2) return true;
+  if (backward) return false;
+  return n_items / kItemsPerWarp < (long long)sm_count() * resident_per_sm * kD32Warps;
+}
+
+int split_grid(long long n_items, int resident_per_sm) {
+  long long ctas = (n_items + kD32Warps - 1) / kD32Warps;
+  const long long cap = (long long)sm_count() * resident_per_sm * 8;
+  if (ctas > cap) ctas = cap;
+  if (ctas < 1) ctas = 1;
+  return (int)ctas;
+}
+
+constexpr size_t kSplitSmem = (size_t)kD32Warps * kMaxLPD32 * 16;
+
+template <typename VT, bool kFuse = false>
+int launch_fwd_d32(D32Params& p, cudaStream_t st, bool* split = nullptr) {
   const int LP = p.L * p.P;
   p.n_items = (long long)p.N * p.Lq * p.M;
+  const bool sp = use_split(p.n_items, MSDA_FWD_MINB, false);
+  if (split) *split = sp;
+  if (sp) {
+    fwd_d32_split_kernel<VT, kFuse><<<split_grid(p.n_items, 4), kD32Threads, kSplitSmem, st>>>(p);
+    return finish_launch(1);
+  }
   const int grid = d32_grid(p.n_items, MSDA_FWD_MINB, MSDA_FWD_WAVES);
   if (p.L == 4 && p.P == 4 && p.M == 8) {   // the shipped geometry (util/settings.py:102-120)
-    fwd_d32_kernel<VT, 4, 4, 8><<<grid, kD32Threads, d32_smem(LP), st>>>(p);
+    fwd_d32_kernel<VT, 4, 4, 8, kFuse><<<grid, kD32Threads, d32_smem(LP), st>>>(p);
   } else {
-    fwd_d32_kernel<VT, 0, 0, 0><<<grid, kD32Threads, d32_smem(LP), st>>>(p);
+    fwd_d32_kernel<VT, 0, 0, 0, kFuse><<<grid, kD32Threads, d32_smem(LP), st>>>(p);
   }
   return finish_launch(1);
 }
 
-template <typename VT, typename GT>
-int launch_bwd_d32(D32Params& p, cudaStream_t st) {
+template <typename VT, typename GT, bool kFuse = false>
+int launch_bwd_d32(D32Params& p, cudaStream_t st, bool* split = nullptr) {
   const int LP = p.L * p.P;
   p.n_items = (long long)p.N * p.Lq * p.M;
+  const bool sp = !kFuse && use_split(p.n_items, MSDA_BWD_MINB, true);
+  if (split) *split = sp;
+  if (sp) {
+    bwd_d32_split_kernel<VT, GT><<<split_grid(p.n_items, 3), kD32Threads, kSplitSmem, st>>>(p);
+    return finish_launch(1);
+  }
   const int grid = d32_grid(p.n_items, MSDA_BWD_MINB, MSDA_BWD_WAVES);
   if (p.L == 4 && p.P == 4 && p.M == 8) {
-    bwd_d32_kernel<VT, GT, 4, 4, 8><<<grid, kD32Threads, d32_smem(LP), st>>>(p);
+    bwd_d32_kernel<VT, GT, 4, 4, 8, kFuse><<<grid, kD32Threads, d32_smem(LP), st>>>(p);
   } else {
-    bwd_d32_kernel<VT, GT, 0, 0, 0><<<grid, kD32Threads, d32_smem(LP), st>>>(p);
+    bwd_d32_kernel<VT, GT, 0, 0, 0, kFuse><<<grid, kD32Threads, d32_smem(LP), st>>>(p);
   }
   return finish_launch(1);
 }
@@ -180,6 +216,11 @@ int msda_b200_set_option(const char* key, int value) {
     g_bf16_direct.store(value);
     return MSDA_OK;
   }
+  if (!strcmp(key, "split_mode")) {
+    if (value < 0 || value > 2) return MSDA_ERR_BAD_OPTION;
+    g_split_mode.store(value);
+    return MSDA_OK;
+  }
   return MSDA_ERR_BAD_OPTION;
 }
 
@@ -188,6 +229,7 @@ int msda_b200_get_option(const char* key, int* value) {
   if (!strcmp(key, "fwd_path")) { *value = g_fwd_path.load(); return MSDA_OK; }
   if (!strcmp(key, "bwd_path")) { *value = g_bwd_path.load(); return MSDA_OK; }
   if (!strcmp(key, "bf16_direct_red")) { *value = g_bf16_direct.load(); return MSDA_OK; }
+  if (!strcmp(key, "split_mode")) { *value = g_split_mode.load(); return MSDA_OK; }
   return MSDA_ERR_BAD_OPTION;
 }
 
@@ -220,8 +262,10 @@ int msda_fwd_f32(const float* value, const int64_t* shapes, const int64_t* lsi, 
     D32Params p{};
     p.value = value; p.shapes = shapes; p.lsi = lsi; p.loc = loc; p.aw = aw; p.out = out;
     p.N = N; p.S = S; p.M = M; p.L = L; p.Lq = Lq; p.P = P;
-    g_last_path[0] = "fwd_d32_f32";
-    return launch_fwd_d32<float>(p, st);
+    bool sp = false;
+    rc = launch_fwd_d32<float>(p, st, &sp);
+    g_last_path[0] = sp ? "fwd_d32_split_f32" : "fwd_d32_f32";
+    return rc;
   }
   g_last_path[0] = "fwd_generic_f32";
   return fwd_any<float>(value, shapes, lsi, loc, aw, N, S, M, D, L, Lq, P, out, st);
@@ -267,8 +311,10 @@ int msda_fwd_bf16(const uint16_t* value, const int64_t* shapes, const int64_t* l
   D32Params p{};
   p.value = value; p.shapes = shapes; p.lsi = lsi; p.loc = loc; p.aw = aw; p.out = out;
   p.N = N; p.S = S; p.M = M; p.L = L; p.Lq = Lq; p.P = P;
-  g_last_path[0] = "fwd_d32_bf16";
-  return launch_fwd_d32<__nv_bfloat16>(p, st);
+  bool sp = false;
+  rc = launch_fwd_d32<__nv_bfloat16>(p, st, &sp);
+  g_last_path[0] = sp ? "fwd_d32_split_bf16" : "fwd_d32_bf16";
+  return rc;
 }
 
 // ---- backward -----------------------------------------------------------------------------
@@ -292,8 +338,10 @@ int msda_bwd_f32(const float* go, const float* value, const int64_t* shapes, con
     p.value = value; p.shapes = shapes; p.lsi = lsi; p.loc = loc; p.aw = aw; p.grad_out = go;
     p.grad_value = gv; p.grad_loc = gl; p.grad_aw = ga;
     p.N = N; p.S = S; p.M = M; p.L = L; p.Lq = Lq; p.P = P;
-    g_last_path[1] = "bwd_d32_f32";
-    return launch_bwd_d32<float, float>(p, st);
+    bool sp = false;
+    rc = launch_bwd_d32<float, float>(p, st, &sp);
+    g_last_path[1] = sp ? "bwd_d32_split_f32" : "bwd_d32_f32";
+    return rc;
   }
   g_last_path[1] = "bwd_generic_f32";
   return bwd_any<float>(go, value, shapes, lsi, loc, aw, N, S, M, D, L, Lq, P, gv, gl, ga, st);
@@ -348,6 +396,56 @@ int msda_bwd_bf16(const float* go, const uint16_t* value, const int64_t* shapes,
   p.grad_value = gv;
   g_last_path[1] = "bwd_d32_bf16";
   return launch_bwd_d32<__nv_bfloat16, __nv_bfloat16>(p, st);
+}
+
+// ---- fused prologue -----------------------------------------------------
+
+int msda_fused_fwd_f32(const float* value, const int64_t* shapes, const int64_t* lsi, const float* ref,
+                       const float* offsets, const float* logits, int N, int S, int M, int D, int L,
+                       int Lq, int P, float* out, void* stream) {
+  int rc = check_dims(N, S, M, D, L, Lq, P);
+  if (rc) return rc;
+  if (nothing_to_do(N, M, D, Lq)) return MSDA_OK;
+  if (!out) return MSDA_ERR_NULL_POINTER;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (L == 0 || P == 0 || S == 0) {
+    const cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float) * (size_t)N * Lq * M * D, st);
+    return e == cudaSuccess ? MSDA_OK : (int)e;
+  }
+  if (!value || !shapes || !lsi || !ref || !offsets || !logits) return MSDA_ERR_NULL_POINTER;
+  if (!d32_eligible(S, M, D, L, P)) return MSDA_ERR_UNSUPPORTED;
+  if (!aligned(value, 16) || !aligned(out, 16) || !aligned(offsets, 8) || !aligned(ref, 8) || !aligned(logits, 4) ||
+      !aligned(shapes, 8) || !aligned(lsi, 8))
+    return MSDA_ERR_MISALIGNED;
+  D32Params p{};
+  p.value = value; p.shapes = shapes; p.lsi = lsi; p.loc = offsets; p.aw = logits; p.ref = ref; p.out = out;
+  p.N = N; p.S = S; p.M = M; p.L = L; p.Lq = Lq; p.P = P;
+  bool sp = false;
+  rc = launch_fwd_d32<float, true>(p, st, &sp);
+  g_last_path[0] = sp ? "fwd_d32_split_fused_f32" : "fwd_d32_fused_f32";
+  return rc;
+}
+
+int msda_fused_bwd_f32(const float* go, const float* value, const int64_t* shapes, const int64_t* lsi,
+                       const float* ref, const float* offsets, const float* logits, int N, int S, int M,
+                       int D, int L, int Lq, int P, float* gv, float* g_offsets, float* g_logits,
+                       float* g_ref, void* stream) {
+  int rc = check_dims(N, S, M, D, L, Lq, P);
+  if (rc) return rc;
+  if (nothing_to_do(N, M, D, Lq) || L == 0 || P == 0 || S == 0) return MSDA_OK;
+  if (!go || !value || !shapes || !lsi || !ref || !offsets || !logits || !gv || !g_offsets || !g_logits)
+    return MSDA_ERR_NULL_POINTER;
+  if (!d32_eligible(S, M, D, L, P)) return MSDA_ERR_UNSUPPORTED;
+  if (!aligned(go, 16) || !aligned(value, 16) || !aligned(gv, 16) || !aligned(offsets, 8) || !aligned(ref, 8) ||
+      !aligned(logits, 4) || !aligned(g_offsets, 8) || !aligned(g_logits, 4) || (g_ref && !aligned(g_ref, 4)) ||
+      !aligned(shapes, 8) || !aligned(lsi, 8))
+    return MSDA_ERR_MISALIGNED;
+  D32Params p{};
+  p.value = value; p.shapes = shapes; p.lsi = lsi; p.loc = offsets; p.aw = logits; p.ref = ref; p.grad_out = go;
+  p.grad_value = gv; p.grad_loc = g_offsets; p.grad_aw = g_logits; p.grad_ref = g_ref;
+  p.N = N; p.S = S; p.M = M; p.L = L; p.Lq = Lq; p.P = P;
+  g_last_path[1] = "bwd_d32_fused_f32";
+  return launch_bwd_d32<float, float, true>(p, (cudaStream_t)stream);
 }
 
 // ---- parity probe -------------------------------------------------------------------------

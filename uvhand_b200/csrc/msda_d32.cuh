@@ -95,6 +95,12 @@ struct D32Params {
   float* grad_aw;
   int N, S, M, L, Lq, P;
   long long n_items;
+  // Fused prologue (kFuse kernels): `loc` then holds the RAW sampling offsets [N,Lq,M,L,P,2] and
+  // `aw` the RAW attention logits [N,Lq,M,L*P]; ref = reference points [N,Lq,L,2].  In the backward
+  // grad_loc / grad_aw then receive d/d offsets and d/d logits, and grad_ref (optional, zeroed by
+  // the caller) d/d reference points.
+  const float* ref;
+  float* grad_ref;
 };
 
 __host__ __device__ constexpr int rec_stride(int LP) { return LP | 1; }  // odd => conflict-free groups
@@ -111,10 +117,11 @@ __device__ __forceinline__ void load_level_tab(LevelTab& tab, const D32Params& p
 // Phase A for one sample.
 //   forward : f = (a*hh, a*lh, lw)      backward : f = (lh, lw, a)
 // A rejected sample gets mask 0 and zero payload: phase B then loads nothing and adds zero.
-template <bool kBackward>
+template <bool kBackward, bool kKeepWeight = false>
 __device__ __forceinline__ int4 make_record(float x, float y, float a, int H, int W, int start, int M) {
   SampleGeom<float> g;
-  if (!sample_geom<float>(x, y, H, W, g)) return make_int4(0, 0, 0, 0);
+  // (fused backward: the softmax gradient needs the weight of rejected samples too)
+  if (!sample_geom<float>(x, y, H, W, g)) return make_int4(0, 0, 0, kKeepWeight ? __float_as_int(a) : 0);
   const int row_m = (start + g.h_low * W + g.w_low) * M;  // may be negative at the top/left border
   int4 r;
   r.x = row_m * 16 + (int)g.mask;
@@ -130,23 +137,75 @@ __device__ __forceinline__ int4 make_record(float x, float y, float a, int H, in
   return r;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fused prologue: what MSDeformAttn.forward does between its Linear layers and the operator
+// (/root/reference/models/ops/modules/ms_deform_attn.py:100-108), done in phase A instead of in
+// separate elementwise kernels that write locations / weights to HBM only to be read back here:
+//   attention_weights = softmax(logits over L*P)                                   (:101-102)
+//   sampling_locations = reference_points + sampling_offsets / (W_l, H_l)          (:104-108)
+// Location arithmetic is torch's, operation for operation (one correctly rounded division, one
+// correctly rounded addition, no contraction), so corner indices are bit-identical to the unfused path.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 fused_location(const D32Params& p, long long item, int l, float2 off,
+                                                 int H, int W) {
+  const float2 r = __ldg(reinterpret_cast<const float2*>(p.ref) + (item / p.M) * p.L + l);
+  return make_float2(__fadd_rn(r.x, __fdiv_rn(off.x, (float)W)), __fadd_rn(r.y, __fdiv_rn(off.y, (float)H)));
+}
+
+// softmax weight of this lane's logit within an aligned segment of kSeg lanes (kSeg a power of two);
+// dead lanes pass -inf and get 0.
+template <int kSeg>
+__device__ __forceinline__ float segment_softmax(float logit) {
+  float m = logit;
+#pragma unroll
+  for (int o = 1; o < kSeg; o <<= 1) m = fmaxf(m, __shfl_xor_sync(kFull, m, o));
+  const float e = (logit == -INFINITY) ? 0.f : expf(logit - m);
+  float sum = e;
+#pragma unroll
+  for (int o = 1; o < kSeg; o <<= 1) sum += __shfl_xor_sync(kFull, sum, o);
+  return __fdiv_rn(e, sum);
+}
+
+// any L*P: every sample thread walks its item's logits (L1-resident) -- not the shipped geometry
+__device__ __forceinline__ float looped_softmax(const float* logits, int LP, float mine) {
+  float m = -INFINITY;
+  for (int j = 0; j < LP; ++j) m = fmaxf(m, __ldg(logits + j));
+  float sum = 0.f;
+  for (int j = 0; j < LP; ++j) sum += expf(__ldg(logits + j) - m);
+  return __fdiv_rn(expf(mine - m), sum);
+}
+
 // Phase A for the whole warp pass: 4*LP samples over 32 lanes, coalesced loc / weight loads.
-template <bool kBackward>
+// kLPc: compile-time L*P (0 = runtime).  The fused softmax runs on shuffles when an item's logits
+// occupy an aligned power-of-two run of lanes and every lane makes the same number of trips.
+template <bool kBackward, bool kFuse, int kLPc>
 __device__ __forceinline__ void geometry_phase(int4* warp_recs, const D32Params& p, const LevelTab& tab,
                                                long long item0, int LP, int lane) {
+  constexpr bool kSegment = kFuse && kLPc > 0 && (kLPc & (kLPc - 1)) == 0 && (kItemsPerWarp * kLPc) % kWarp == 0;
   const int n_samples = kItemsPerWarp * LP;
   const int stride = rec_stride(LP);
   const long long s_base = item0 * LP;
   const long long s_end = p.n_items * LP;
   for (int s = lane; s < n_samples; s += kWarp) {
     const long long gs = s_base + s;
-    if (gs >= s_end) break;
+    const bool in = gs < s_end;
+    if (!kSegment && !in) break;
     const int grp = s / LP;
     const int ls = s - grp * LP;
     const int l = ls / p.P;
-    const float2 xy = ld_stream(reinterpret_cast<const float2*>(p.loc) + gs);
-    const float a = ld_stream(p.aw + gs);
-    warp_recs[grp * stride + ls] = make_record<kBackward>(xy.x, xy.y, a, tab.H[l], tab.W[l], tab.start[l], p.M);
+    float2 xy = make_float2(0.f, 0.f);
+    float a = -INFINITY;
+    if (in) {
+      xy = ld_stream(reinterpret_cast<const float2*>(p.loc) + gs);
+      a = ld_stream(p.aw + gs);
+    }
+    if (kFuse) {
+      a = kSegment ? segment_softmax<(kSegment ? kLPc : 1)>(a) : looped_softmax(p.aw + (gs - ls), LP, a);
+      if (in) xy = fused_location(p, item0 + grp, l, xy, tab.H[l], tab.W[l]);
+    }
+    if (in)
+      warp_recs[grp * stride + ls] =
+          make_record<kBackward, kFuse && kBackward>(xy.x, xy.y, a, tab.H[l], tab.W[l], tab.start[l], p.M);
   }
 }
 
@@ -170,18 +229,26 @@ struct RawSamples {
       }
     }
   }
-  template <bool kBackward, int kP>
+  template <bool kBackward, int kP, bool kFuse>
   __device__ __forceinline__ void park(int4* warp_recs, const D32Params& p, const LevelTab& tab,
                                        long long item0, int lane, int M) const {
     const long long s_base = item0 * kLP, s_end = p.n_items * kLP;
 #pragma unroll
     for (int i = 0; i < kPerLane; ++i) {
       const int s = lane + i * kWarp;
-      if (s_base + s < s_end) {
-        const int grp = s / kLP, ls = s % kLP, l = ls / kP;
-        warp_recs[grp * rec_stride(kLP) + ls] =
-            make_record<kBackward>(xy[i].x, xy[i].y, a[i], tab.H[l], tab.W[l], tab.start[l], M);
+      const bool in = s_base + s < s_end;
+      const int grp = s / kLP, ls = s % kLP, l = ls / kP;
+      float2 loc = xy[i];
+      float w = a[i];
+      if (kFuse) {
+        // the L*P logits of an item sit in L*P consecutive, aligned lanes
+        static_assert(!kFuse || (kLP & (kLP - 1)) == 0, "fused pipeline needs a power-of-two L*P");
+        w = segment_softmax<kLP>(in ? w : -INFINITY);
+        if (in) loc = fused_location(p, item0 + grp, l, loc, tab.H[l], tab.W[l]);
       }
+      if (in)
+        warp_recs[grp * rec_stride(kLP) + ls] =
+            make_record<kBackward, kFuse && kBackward>(loc.x, loc.y, w, tab.H[l], tab.W[l], tab.start[l], M);
     }
   }
 };
@@ -212,7 +279,7 @@ struct LevelStride {
 // ---------------------------------------------------------------------------------------------
 // Forward
 // ---------------------------------------------------------------------------------------------
-template <typename VT, int kL, int kP, int kM>  // compile-time levels / points / heads (0: runtime)
+template <typename VT, int kL, int kP, int kM, bool kFuse = false>  // compile-time levels / points / heads (0: runtime)
 __global__ void __launch_bounds__(kD32Threads, MSDA_FWD_MINB)
 fwd_d32_kernel(const D32Params p) {
   using C = Chunk<VT>;
@@ -235,17 +302,18 @@ fwd_d32_kernel(const D32Params p) {
 
   const long long n_pass = (p.n_items + kItemsPerWarp - 1) / kItemsPerWarp;
   const long long pass_stride = (long long)gridDim.x * kD32Warps;
-  constexpr bool kPipe = kStatic && MSDA_FWD_PREFETCH && (kItemsPerWarp * kL * kP) % kWarp == 0;
+  constexpr bool kPipe = kStatic && MSDA_FWD_PREFETCH && (kItemsPerWarp * kL * kP) % kWarp == 0 &&
+                         (!kFuse || ((kL * kP) & (kL * kP - 1)) == 0);
   RawSamples<kPipe ? kL * kP : kWarp> raw;
   const long long pass0 = (long long)blockIdx.x * kD32Warps + warp;
   if (kPipe && pass0 < n_pass) raw.load(p, pass0 * kItemsPerWarp, lane);
   for (long long pass = pass0; pass < n_pass; pass += pass_stride) {
     const long long item0 = pass * kItemsPerWarp;
     if (kPipe) {
-      raw.template park<false, (kP > 0 ? kP : 1)>(warp_recs, p, tab, item0, lane, M);
+      raw.template park<false, (kP > 0 ? kP : 1), kFuse>(warp_recs, p, tab, item0, lane, M);
       if (pass + pass_stride < n_pass) raw.load(p, (pass + pass_stride) * kItemsPerWarp, lane);
     } else {
-      geometry_phase<false>(warp_recs, p, tab, item0, LP, lane);
+      geometry_phase<false, kFuse, (kStatic ? kL * kP : 0)>(warp_recs, p, tab, item0, LP, lane);
     }
     __syncwarp();
 
@@ -364,7 +432,7 @@ __device__ __forceinline__ void bwd_sample(const int4 r, const typename Chunk<VT
 // VT: storage type of value; GT: type grad_value is accumulated in (float: red.v4.f32 -- also used
 // for bf16 values accumulating into an fp32 scratch; __nv_bfloat16: red.v2.bf16x2 straight into a
 // bf16 grad_value, faster but every add rounds the running sum to 8 bits).
-template <typename VT, typename GT, int kL, int kP, int kM>
+template <typename VT, typename GT, int kL, int kP, int kM, bool kFuse = false>
 __global__ void __launch_bounds__(kD32Threads, MSDA_BWD_MINB)
 bwd_d32_kernel(const D32Params p) {
   using C = Chunk<VT>;
@@ -382,21 +450,23 @@ bwd_d32_kernel(const D32Params p) {
   const int group = lane >> 3, sub = lane & 7;
   int4* warp_recs = reinterpret_cast<int4*>(smem_raw) + warp * (kItemsPerWarp * stride);
   const int4* my_recs = warp_recs + group * stride;
+  int4* my_recs_w = warp_recs + group * stride;
   const int M = (MSDA_STATIC_M && kM > 0) ? kM : p.M;   // compile-time M turns the x+1 corner into an immediate offset
 
   const long long n_pass = (p.n_items + kItemsPerWarp - 1) / kItemsPerWarp;
   const long long pass_stride = (long long)gridDim.x * kD32Warps;
-  constexpr bool kPipe = kStatic && MSDA_BWD_PREFETCH && (kItemsPerWarp * kL * kP) % kWarp == 0;
+  constexpr bool kPipe = kStatic && MSDA_BWD_PREFETCH && (kItemsPerWarp * kL * kP) % kWarp == 0 &&
+                         (!kFuse || ((kL * kP) & (kL * kP - 1)) == 0);
   RawSamples<kPipe ? kL * kP : kWarp> raw;
   const long long pass0 = (long long)blockIdx.x * kD32Warps + warp;
   if (kPipe && pass0 < n_pass) raw.load(p, pass0 * kItemsPerWarp, lane);
   for (long long pass = pass0; pass < n_pass; pass += pass_stride) {
     const long long item0 = pass * kItemsPerWarp;
     if (kPipe) {
-      raw.template park<true, (kP > 0 ? kP : 1)>(warp_recs, p, tab, item0, lane, M);
+      raw.template park<true, (kP > 0 ? kP : 1), kFuse>(warp_recs, p, tab, item0, lane, M);
       if (pass + pass_stride < n_pass) raw.load(p, (pass + pass_stride) * kItemsPerWarp, lane);
     } else {
-      geometry_phase<true>(warp_recs, p, tab, item0, LP, lane);
+      geometry_phase<true, kFuse, (kStatic ? kL * kP : 0)>(warp_recs, p, tab, item0, LP, lane);
     }
     __syncwarp();
 
@@ -432,9 +502,29 @@ bwd_d32_kernel(const D32Params p) {
           const float tx = group8_sum4(px, sub);
           const float ty = group8_sum4(py, sub);
           const int s = s0 + (sub >> 1);
-          if (live) {
-            if (sub & 1) st_stream(ga_out + s, ta);
-            else st_stream(gl_out + s, make_float2(tx, ty));
+          if (!kFuse) {
+            if (live) {
+              if (sub & 1) st_stream(ga_out + s, ta);
+              else st_stream(gl_out + s, make_float2(tx, ty));
+            }
+          } else {
+            // d loc / d offset = 1 / (W, H); d/d reference point = sum over this level's points (and over
+            // heads: accumulated with scalar reductions, 2 per (query, head, level)); the gradient of
+            // the post-softmax weight is parked in the record for the softmax backward below.
+            if (live) {
+              if (sub & 1) my_recs_w[s].y = __float_as_int(ta);
+              else st_stream(gl_out + s, make_float2(__fdiv_rn(tx, Wf), __fdiv_rn(ty, Hf)));
+            }
+            if (p.grad_ref) {
+              float rx = (sub & 1) ? 0.f : tx, ry = (sub & 1) ? 0.f : ty;
+              rx = group8_sum(rx);
+              ry = group8_sum(ry);
+              if (live && sub == 0) {
+                float* gr = p.grad_ref + ((item / M) * p.L + l) * 2;
+                atomicAdd(gr, rx);
+                atomicAdd(gr + 1, ry);
+              }
+            }
           }
         }
       }
@@ -448,9 +538,161 @@ bwd_d32_kernel(const D32Params p) {
         px = group8_sum(px);
         py = group8_sum(py);
         if (live && sub == (s & 7)) {
-          st_stream(gl_out + s, make_float2(px, py));
-          st_stream(ga_out + s, pa);
+          if (!kFuse) {
+            st_stream(gl_out + s, make_float2(px, py));
+            st_stream(ga_out + s, pa);
+          } else {
+            const float Wf = (float)tab.W[l], Hf = (float)tab.H[l];
+            st_stream(gl_out + s, make_float2(__fdiv_rn(px, Wf), __fdiv_rn(py, Hf)));
+            my_recs_w[s].y = __float_as_int(pa);
+            if (p.grad_ref) {
+              float* gr = p.grad_ref + ((item / M) * p.L + l) * 2;
+              atomicAdd(gr, px);
+              atomicAdd(gr + 1, py);
+            }
+          }
         }
+      }
+    }
+    if (kFuse) {
+      // softmax backward (modules/ms_deform_attn.py:102): d/d logit_s = a_s * (ga_s - sum_j a_j * ga_j),
+      // a_s in record.w (kept for rejected samples too), ga_s parked in record.y above.
+      __syncwarp();
+      float part = 0.f;
+      for (int s = sub; s < LP; s += 8) {
+        const int4 r = my_recs[s];
+        part = fmaf(__int_as_float(r.w), __int_as_float(r.y), part);
+      }
+      const float dot = group8_sum(part);
+      if (live)
+        for (int s = sub; s < LP; s += 8) {
+          const int4 r = my_recs[s];
+          st_stream(ga_out + s, __int_as_float(r.w) * (__int_as_float(r.y) - dot));
+        }
+    }
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Small problems (decoder queries: a few thousand (query, head) items): "split" kernels.
+//
+// With 4 items per warp a 900-query decoder call fills a quarter of the machine and every warp walks
+// its 16 samples one after the other, each a cold L2/HBM round trip: the call costs the LATENCY of
+// that chain (~25 us), not bandwidth.  Here a warp takes ONE item and its four 8-lane groups take
+// every fourth sample, so the chain is 4x shorter and there are 4x as many warps in flight; the
+// four partial rows are summed with two shuffles per register.  Any L, P with L*P <= 32; runtime M.
+// ---------------------------------------------------------------------------------------------
+template <bool kBackward, bool kFuse>
+__device__ __forceinline__ void split_geometry(int4* warp_recs, const D32Params& p, const LevelTab& tab,
+                                               long long item, int LP, int lane) {
+  const bool in = lane < LP;
+  const long long gs = item * LP + lane;
+  const int l = in ? lane / p.P : 0;
+  float2 xy = make_float2(0.f, 0.f);
+  float a = -INFINITY;
+  if (in) {
+    xy = ld_stream(reinterpret_cast<const float2*>(p.loc) + gs);
+    a = ld_stream(p.aw + gs);
+  }
+  if (kFuse) {
+    a = segment_softmax<kWarp>(a);     // the item's logits are lanes [0, LP); the rest pass -inf
+    if (in) xy = fused_location(p, item, l, xy, tab.H[l], tab.W[l]);
+  }
+  if (in)
+    warp_recs[lane] = make_record<kBackward, kFuse && kBackward>(xy.x, xy.y, a, tab.H[l], tab.W[l], tab.start[l], p.M);
+}
+
+template <typename VT, bool kFuse = false>
+__global__ void __launch_bounds__(kD32Threads, 4)
+fwd_d32_split_kernel(const D32Params p) {
+  using C = Chunk<VT>;
+  using Vec = typename C::Vec;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ LevelTab tab;
+  load_level_tab(tab, p);
+  const int P = p.P, LP = p.L * p.P, M = p.M;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int group = lane >> 3, sub = lane & 7;
+  int4* warp_recs = reinterpret_cast<int4*>(smem_raw) + warp * kMaxLPD32;
+  for (long long item = (long long)blockIdx.x * kD32Warps + warp; item < p.n_items;
+       item += (long long)gridDim.x * kD32Warps) {
+    split_geometry<false, kFuse>(warp_recs, p, tab, item, LP, lane);
+    __syncwarp();
+    const int m = (int)(item % M);
+    const int b = (int)(item / ((long long)M * p.Lq));
+    const Vec* vb = reinterpret_cast<const Vec*>(p.value) + ((long long)b * p.S * M + m) * 8 + sub;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+    for (int s = group; s < LP; s += kItemsPerWarp) {
+      const int4 r = warp_recs[s];
+      const int wm = tab.W[s / P] * M;
+      const int row = r.x >> 4;
+      const float ah = __int_as_float(r.y), al = __int_as_float(r.z), lw = __int_as_float(r.w);
+      const float w2 = ah * lw, w4 = al * lw;
+      const float w1 = ah - w2, w3 = al - w4;
+      const Vec* r0 = vb + (long long)row * 8;
+      const Vec* r1 = r0 + (long long)wm * 8;
+      float4 v1 = make_float4(0.f, 0.f, 0.f, 0.f), v2 = v1, v3 = v1, v4 = v1;
+      if (r.x & 1) v1 = C::load(r0);
+      if (r.x & 2) v2 = C::load(r0 + M * 8);
+      if (r.x & 4) v3 = C::load(r1);
+      if (r.x & 8) v4 = C::load(r1 + M * 8);
+      fma4(acc, w1, v1);
+      fma4(acc, w2, v2);
+      fma4(acc, w3, v3);
+      fma4(acc, w4, v4);
+    }
+#pragma unroll
+    for (int o = 8; o <= 16; o <<= 1) {
+      acc.x += __shfl_xor_sync(kFull, acc.x, o);
+      acc.y += __shfl_xor_sync(kFull, acc.y, o);
+      acc.z += __shfl_xor_sync(kFull, acc.z, o);
+      acc.w += __shfl_xor_sync(kFull, acc.w, o);
+    }
+    if (group == 0) st_stream(reinterpret_cast<float4*>(p.out) + item * 8 + sub, acc);
+    __syncwarp();
+  }
+}
+
+template <typename VT, typename GT>
+__global__ void __launch_bounds__(kD32Threads, 3)
+bwd_d32_split_kernel(const D32Params p) {
+  using Vec = typename Chunk<VT>::Vec;
+  using GVec = typename Chunk<GT>::Vec;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ LevelTab tab;
+  load_level_tab(tab, p);
+  const int P = p.P, LP = p.L * p.P, M = p.M;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int group = lane >> 3, sub = lane & 7;
+  int4* warp_recs = reinterpret_cast<int4*>(smem_raw) + warp * kMaxLPD32;
+  for (long long item = (long long)blockIdx.x * kD32Warps + warp; item < p.n_items;
+       item += (long long)gridDim.x * kD32Warps) {
+    split_geometry<true, false>(warp_recs, p, tab, item, LP, lane);
+    __syncwarp();
+    const int m = (int)(item % M);
+    const int b = (int)(item / ((long long)M * p.Lq));
+    const long long head_off = ((long long)b * p.S * M + m) * 8 + sub;
+    const Vec* vb = reinterpret_cast<const Vec*>(p.value) + head_off;
+    GVec* gvb = reinterpret_cast<GVec*>(p.grad_value) + head_off;
+    const float4 g = ld_stream(reinterpret_cast<const float4*>(p.grad_out) + item * 8 + sub);
+    float2* gl_out = reinterpret_cast<float2*>(p.grad_loc) + item * LP;
+    float* ga_out = p.grad_aw + item * LP;
+    // every group runs the same number of rounds: the shuffles below are warp-wide
+    for (int s0 = 0; s0 < LP; s0 += kItemsPerWarp) {
+      const int s = s0 + group;
+      const bool live = s < LP;
+      const int l = live ? s / P : 0;
+      const int4 r = live ? warp_recs[s] : make_int4(0, 0, 0, 0);
+      float pa, px, py;
+      bwd_sample<VT, GT>(r, vb, gvb, g, M, tab.W[l] * M, (float)tab.W[l], (float)tab.H[l], live, pa, px, py);
+      pa = group8_sum(pa);
+      px = group8_sum(px);
+      py = group8_sum(py);
+      if (live && sub == 0) {
+        st_stream(gl_out + s, make_float2(px, py));
+        st_stream(ga_out + s, pa);
       }
     }
     __syncwarp();

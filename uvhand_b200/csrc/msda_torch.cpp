@@ -191,10 +191,90 @@ std::vector<at::Tensor> ms_deform_attn_backward(const at::Tensor& value, const a
   return {grad_value, grad_loc, grad_aw};
 }
 
+// ---- fused prologue: softmax + location arithmetic folded into the operator -------------------
+// Not in the reference extension; replaces, inside MSDeformAttn.forward, the elementwise steps of
+// /root/reference/models/ops/modules/ms_deform_attn.py:100-108.
+namespace {
+
+Sizes fused_checks(const at::Tensor& value, const at::Tensor& spatial_shapes, const at::Tensor& level_start_index,
+                   const at::Tensor& ref, const at::Tensor& offsets, const at::Tensor& logits) {
+  TORCH_CHECK(value.is_cuda(), "Not implemented on the CPU");
+  for (const at::Tensor* t : {&value, &spatial_shapes, &level_start_index, &ref, &offsets, &logits}) {
+    TORCH_CHECK(t->is_contiguous(), "fused MSDeformAttn: every tensor has to be contiguous");
+    TORCH_CHECK(t->is_cuda() && t->device() == value.device(), "fused MSDeformAttn: all tensors must be on value's device");
+  }
+  TORCH_CHECK(value.scalar_type() == at::kFloat && ref.scalar_type() == at::kFloat &&
+                  offsets.scalar_type() == at::kFloat && logits.scalar_type() == at::kFloat,
+              "fused MSDeformAttn is float32 only");
+  TORCH_CHECK(spatial_shapes.scalar_type() == at::kLong && level_start_index.scalar_type() == at::kLong,
+              "spatial_shapes / level_start_index must be int64");
+  TORCH_CHECK(value.dim() == 4 && offsets.dim() == 6 && offsets.size(5) == 2, "value [N,S,M,D], sampling_offsets [N,Lq,M,L,P,2]");
+  Sizes s;
+  s.N = (int)value.size(0); s.S = (int)value.size(1); s.M = (int)value.size(2); s.D = (int)value.size(3);
+  s.L = (int)spatial_shapes.size(0); s.Lq = (int)offsets.size(1); s.P = (int)offsets.size(4);
+  TORCH_CHECK(offsets.size(0) == s.N && offsets.size(2) == s.M && offsets.size(3) == s.L,
+              "sampling_offsets shape does not match value / spatial_shapes");
+  TORCH_CHECK(logits.numel() == (int64_t)s.N * s.Lq * s.M * s.L * s.P, "attn_logits must be [N, Lq, M, L*P]");
+  TORCH_CHECK(ref.dim() == 4 && ref.size(0) == s.N && ref.size(1) == s.Lq && ref.size(2) == s.L && ref.size(3) == 2,
+              "reference_points must be [N, Lq, L, 2]");
+  TORCH_CHECK(level_start_index.numel() == s.L, "level_start_index must have one entry per level");
+  return s;
+}
+
+}  // namespace
+
+at::Tensor ms_deform_attn_fused_forward(const at::Tensor& value, const at::Tensor& spatial_shapes,
+                                        const at::Tensor& level_start_index, const at::Tensor& reference_points,
+                                        const at::Tensor& sampling_offsets, const at::Tensor& attn_logits) {
+  const Sizes s = fused_checks(value, spatial_shapes, level_start_index, reference_points, sampling_offsets, attn_logits);
+  const c10::cuda::CUDAGuard guard(value.device());
+  at::Tensor output = at::empty({s.N, s.Lq, s.M, s.D}, value.options());
+  check_rc(msda_fused_fwd_f32(value.data_ptr<float>(), spatial_shapes.data_ptr<int64_t>(),
+                              level_start_index.data_ptr<int64_t>(), reference_points.data_ptr<float>(),
+                              sampling_offsets.data_ptr<float>(), attn_logits.data_ptr<float>(), s.N, s.S, s.M,
+                              s.D, s.L, s.Lq, s.P, output.data_ptr<float>(),
+                              at::cuda::getCurrentCUDAStream().stream()),
+           "ms_deform_attn_fused_forward");
+  return output.view({s.N, s.Lq, s.M * s.D});
+}
+
+// -> [grad_value, grad_sampling_offsets, grad_attn_logits, grad_reference_points (empty tensor if not wanted)]
+std::vector<at::Tensor> ms_deform_attn_fused_backward(const at::Tensor& value, const at::Tensor& spatial_shapes,
+                                                      const at::Tensor& level_start_index,
+                                                      const at::Tensor& reference_points,
+                                                      const at::Tensor& sampling_offsets,
+                                                      const at::Tensor& attn_logits, const at::Tensor& grad_output,
+                                                      const bool want_grad_reference) {
+  const Sizes s = fused_checks(value, spatial_shapes, level_start_index, reference_points, sampling_offsets, attn_logits);
+  TORCH_CHECK(grad_output.is_contiguous() && grad_output.is_cuda() && grad_output.scalar_type() == at::kFloat &&
+                  grad_output.numel() == (int64_t)s.N * s.Lq * s.M * s.D,
+              "grad_output must be a contiguous float32 CUDA tensor [N, Lq, M*D]");
+  const c10::cuda::CUDAGuard guard(value.device());
+  at::Tensor grad_value = at::zeros_like(value);
+  at::Tensor grad_off = at::empty_like(sampling_offsets);
+  at::Tensor grad_logits = at::empty_like(attn_logits);
+  at::Tensor grad_ref = want_grad_reference ? at::zeros_like(reference_points) : at::Tensor();
+  if (s.L == 0 || s.P == 0 || s.S == 0) {
+    grad_off.zero_();
+    grad_logits.zero_();
+  }
+  check_rc(msda_fused_bwd_f32(grad_output.data_ptr<float>(), value.data_ptr<float>(),
+                              spatial_shapes.data_ptr<int64_t>(), level_start_index.data_ptr<int64_t>(),
+                              reference_points.data_ptr<float>(), sampling_offsets.data_ptr<float>(),
+                              attn_logits.data_ptr<float>(), s.N, s.S, s.M, s.D, s.L, s.Lq, s.P,
+                              grad_value.data_ptr<float>(), grad_off.data_ptr<float>(), grad_logits.data_ptr<float>(),
+                              want_grad_reference ? grad_ref.data_ptr<float>() : nullptr,
+                              at::cuda::getCurrentCUDAStream().stream()),
+           "ms_deform_attn_fused_backward");
+  return {grad_value, grad_off, grad_logits, grad_ref};
+}
+
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("ms_deform_attn_forward", &ms_deform_attn_forward, "ms_deform_attn_forward");
   m.def("ms_deform_attn_backward", &ms_deform_attn_backward, "ms_deform_attn_backward");
   // additions (not in the reference module)
+  m.def("ms_deform_attn_fused_forward", &ms_deform_attn_fused_forward, "softmax + location prologue fused in");
+  m.def("ms_deform_attn_fused_backward", &ms_deform_attn_fused_backward, "backward of the fused operator");
   m.def("set_option", [](const std::string& key, int value) {
     check_rc(msda_b200_set_option(key.c_str(), value), "set_option");
   });

@@ -74,3 +74,45 @@ class MSDeformAttnFunction(Function):
             _kernel_value(value, sampling_locations), value_spatial_shapes, value_level_start_index,
             sampling_locations, attention_weights, grad_output.contiguous(), ctx.im2col_step)
         return grad_value, None, None, grad_sampling_loc, grad_attn_weight, None
+
+
+class MSDeformAttnFusedFunction(Function):
+    """The operator with MSDeformAttn.forward's softmax and location arithmetic folded in
+    (/root/reference/models/ops/modules/ms_deform_attn.py:100-108):
+
+        MSDeformAttnFusedFunction.apply(value, value_spatial_shapes, value_level_start_index,
+                                        reference_points,      # [N, Lq, L, 2]
+                                        sampling_offsets,      # [N, Lq, M, L, P, 2]  raw Linear output
+                                        attention_logits)      # [N, Lq, M, L*P]      raw Linear output
+
+    == MSDeformAttnFunction.apply(value, shapes, lsi, reference_points[:, :, None, :, None, :]
+                                  + sampling_offsets / (W_l, H_l), softmax(attention_logits), step)
+    with identical sampling locations (same fp32 operations) and weights equal to rounding.  float32,
+    D = 32, L <= 8, L*P <= 32 only (``fused_supported``); not part of the reference API -- the
+    MSDeformAttn module uses it when constructed with ``fuse_prologue=True``."""
+
+    @staticmethod
+    def forward(ctx, value, value_spatial_shapes, value_level_start_index, reference_points,
+                sampling_offsets, attention_logits):
+        out = MSDA.ms_deform_attn_fused_forward(value, value_spatial_shapes, value_level_start_index,
+                                                reference_points, sampling_offsets, attention_logits)
+        ctx.save_for_backward(value, value_spatial_shapes, value_level_start_index, reference_points,
+                              sampling_offsets, attention_logits)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        value, shapes, lsi, ref, offsets, logits = ctx.saved_tensors
+        want_ref = ctx.needs_input_grad[3]
+        gv, goff, glogit, gref = MSDA.ms_deform_attn_fused_backward(
+            value, shapes, lsi, ref, offsets, logits, grad_output.contiguous(), want_ref)
+        return gv, None, None, (gref if want_ref else None), goff, glogit
+
+
+def fused_supported(value: torch.Tensor, sampling_offsets: torch.Tensor, reference_points: torch.Tensor) -> bool:
+    """Whether the fused kernels serve these operands (else callers use MSDeformAttnFunction)."""
+    return (value.is_cuda and value.dtype == torch.float32 and sampling_offsets.dtype == torch.float32
+            and value.dim() == 4 and value.shape[3] == 32 and sampling_offsets.dim() == 6
+            and sampling_offsets.shape[3] <= 8 and sampling_offsets.shape[3] * sampling_offsets.shape[4] <= 32
+            and reference_points.shape[-1] == 2 and value.shape[1] * value.shape[2] < (1 << 27))

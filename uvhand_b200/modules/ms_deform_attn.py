@@ -20,7 +20,9 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
-from ..functions.ms_deform_attn_func import MSDeformAttnFunction
+import os
+
+from ..functions.ms_deform_attn_func import MSDeformAttnFunction, MSDeformAttnFusedFunction, fused_supported
 
 
 def _power_of_two(n) -> bool:
@@ -30,8 +32,17 @@ def _power_of_two(n) -> bool:
 
 
 class MSDeformAttn(nn.Module):
-    def __init__(self, d_model: int = 256, n_levels: int = 4, n_heads: int = 8, n_points: int = 4):
+    def __init__(self, d_model: int = 256, n_levels: int = 4, n_heads: int = 8, n_points: int = 4,
+                 fuse_prologue: bool | None = None):
+        """``fuse_prologue`` (not in the reference; default off, or env MSDA_B200_FUSE_PROLOGUE=1): let the
+        kernels compute softmax(attention_weights) and reference + offsets / (W, H) themselves
+        instead of materialising sampling_locations / attention_weights.
+        Same parameters, same results to rounding; falls back to the unfused kernels when the fused
+        ones do not serve the operands (channels/head != 32, box references, non-fp32)."""
         super().__init__()
+        if fuse_prologue is None:
+            fuse_prologue = os.environ.get("MSDA_B200_FUSE_PROLOGUE", "0") not in ("", "0", "false", "False")
+        self.fuse_prologue = bool(fuse_prologue)
         if d_model % n_heads != 0:
             raise ValueError(f"d_model must be divisible by n_heads, but got {d_model} and {n_heads}")
         if not _power_of_two(d_model // n_heads):
@@ -105,6 +116,14 @@ class MSDeformAttn(nn.Module):
             n, len_q, self.n_heads, self.n_levels, self.n_points, 2)
         weights = self.attention_weights(query).view(
             n, len_q, self.n_heads, self.n_levels * self.n_points)
+        if self.fuse_prologue and reference_points.shape[-1] in (2, 42):
+            centre = reference_points
+            if reference_points.shape[-1] == 42:     # keypoint centre (ms_deform_attn.py:123-124), [N, Lq, L, 2]
+                centre = torch.stack([reference_points[..., 0::2].mean(-1), reference_points[..., 1::2].mean(-1)], -1)
+            if fused_supported(value, offsets, centre):
+                out = MSDeformAttnFusedFunction.apply(value, input_spatial_shapes, input_level_start_index,
+                                                      centre.to(value.dtype).contiguous(), offsets, weights)
+                return self.output_proj(out)
         weights = F.softmax(weights, -1).view(n, len_q, self.n_heads, self.n_levels, self.n_points)
         locations = self._sampling_locations(reference_points, offsets, input_spatial_shapes)
 
