@@ -727,6 +727,44 @@ def test_module_fused_prologue_equals_unfused(ref_dim):
 
 
 # ------------------------------------------------------------------------------------------------
+# launch hygiene: the entry points never synchronise, so a stack of calls can be
+# captured in a CUDA graph and replayed
+# ------------------------------------------------------------------------------------------------
+
+def test_calls_are_capturable_in_a_cuda_graph():
+    wl = WORKLOADS["c4_dino_decoder"]
+    x = make_inputs(wl, seed=3, device="cuda")
+    dims = wl.dims()
+    out = torch.zeros(wl.N, wl.Lq, wl.M * wl.D, device="cuda")
+    gv, gl, ga = torch.zeros_like(x["value"]), torch.zeros_like(x["loc"]), torch.zeros_like(x["aw"])
+
+    def step(stream):
+        gv.zero_()
+        cabi.forward("f32", x["value"].data_ptr(), x["shapes"].data_ptr(), x["lsi"].data_ptr(), x["loc"].data_ptr(),
+                     x["aw"].data_ptr(), dims, out.data_ptr(), stream)
+        cabi.backward("f32", x["grad_out"].data_ptr(), x["value"].data_ptr(), x["shapes"].data_ptr(), x["lsi"].data_ptr(),
+                      x["loc"].data_ptr(), x["aw"].data_ptr(), dims, gv.data_ptr(), gl.data_ptr(), ga.data_ptr(), stream)
+
+    step(torch.cuda.current_stream().cuda_stream)          # eager reference (also warms the library up)
+    torch.cuda.synchronize()
+    want = [t.clone() for t in (out, gl, ga)]
+    want_gv = gv.clone()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        for _ in range(6):                                 # e.g. the six decoder layers of one model step
+            step(torch.cuda.current_stream().cuda_stream)
+    for t in (out, gl, ga, gv):
+        t.fill_(float("nan"))
+    n0 = cabi.launch_count()
+    graph.replay()
+    torch.cuda.synchronize()
+    assert cabi.launch_count() == n0                       # replay launches nothing through the host path
+    for got, ref in zip((out, gl, ga), want):
+        assert torch.equal(got, ref)
+    close(gv.cpu().numpy(), want_gv.cpu().numpy(), GRAD_RTOL)   # atomics: order may differ between runs
+
+
+# ------------------------------------------------------------------------------------------------
 # host-buffer C ABI (what a non-torch caller binds)
 # ------------------------------------------------------------------------------------------------
 
