@@ -80,10 +80,20 @@ def test_argument_validation_without_gpu():
     # size overflow
     big = 2 ** 31 - 1
     assert L.msda_fwd_f32(None, None, None, None, None, big, big, 8, 32, 4, 5, 4, None, None) == -2
+    # fused prologue entry points: same argument discipline; D != 32 or L*P > 32 is "unsupported", not a fallback
+    assert L.msda_fused_fwd_f32(None, None, None, None, None, None, 0, 10, 8, 32, 4, 5, 4, None, None) == 0
+    assert L.msda_fused_fwd_f32(None, None, None, None, None, None, 1, 10, 8, 32, 4, 5, 4, None, None) == -1
+    assert L.msda_fused_bwd_f32(None, None, None, None, None, None, None, 1, 10, 8, 32, 4, 5, 4,
+                                None, None, None, None, None) == -1
+    import ctypes
+    buf = (ctypes.c_float * 64)()
+    p = ctypes.cast(buf, ctypes.c_void_p)
+    assert L.msda_fused_fwd_f32(p, p, p, p, p, p, 1, 10, 8, 30, 4, 5, 4, p, None) == -4      # D = 30
+    assert L.msda_fused_fwd_f32(p, p, p, p, p, p, 1, 10, 8, 32, 5, 5, 7, p, None) == -4      # L*P = 35
 
 
 def test_options_roundtrip():
-    for key in ("fwd_path", "bwd_path"):
+    for key in ("fwd_path", "bwd_path", "split_mode"):
         assert cabi.get_option(key) == 0
         cabi.set_option(key, 1)
         assert cabi.get_option(key) == 1

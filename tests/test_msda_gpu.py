@@ -300,6 +300,53 @@ def test_shape_sweep(shape, kind):
         check_all(res, ref, 1e-12, 1e-11)
 
 
+@pytest.mark.parametrize("seed", range(12))
+def test_random_geometry_fuzz(seed):
+    """Seeded random problems (ragged level sizes incl. 1xW / Hx1 / 1x1, any M, L, P with D = 32, locations
+    from well outside to well inside, a sprinkle of NaN / inf / exact pixel centres / exact borders) through
+    all three D=32-capable kernel families, against the oracle."""
+    rng = np.random.default_rng(1000 + seed)
+    L = int(rng.integers(1, 9))
+    P = int(rng.integers(1, 32 // L + 1))
+    M = int(rng.integers(1, 10))
+    N = int(rng.integers(1, 4))
+    Lq = int(rng.integers(1, 70))
+    levels = tuple((int(rng.integers(1, 12)), int(rng.integers(1, 12))) for _ in range(L))
+    wl = Workload("fz", N, levels, Lq, M=M, D=32, P=P, loc_dist="uniform")
+    x = np_inputs(wl, 50 + seed, pad_frac=0.0)
+    loc = (rng.random(x["loc"].shape) * 1.6 - 0.3).astype(np.float32)
+    wh = np.array([[w, h] for h, w in levels], np.float32)[None, None, None, :, None, :]
+    flat = loc.reshape(-1, 2)
+    k = flat.shape[0]
+    pick = rng.choice(k, size=max(1, k // 6), replace=False)
+    kinds = rng.integers(0, 6, size=pick.size)
+    lvl_of = np.broadcast_to(np.arange(L)[None, None, None, :, None], loc.shape[:-1]).reshape(-1)
+    for i, kind in zip(pick, kinds):
+        w_, h_ = wh.reshape(-1, 2)[lvl_of[i]]
+        if kind == 0:
+            flat[i] = [np.nan, 0.5]
+        elif kind == 1:
+            flat[i] = [0.5, np.inf if rng.random() < 0.5 else -np.inf]
+        elif kind == 2:   # exact pixel centres
+            flat[i] = [(rng.integers(0, int(w_)) + 0.5) / w_, (rng.integers(0, int(h_)) + 0.5) / h_]
+        elif kind == 3:   # exact pixel edges, including the outer borders 0 and 1
+            flat[i] = [rng.integers(0, int(w_) + 1) / w_, rng.integers(0, int(h_) + 1) / h_]
+        elif kind == 4:   # half a pixel outside: the last accepted / first rejected coordinates
+            flat[i] = [-0.5 / w_, 1.0 + 0.5 / h_]
+        else:
+            flat[i] = [1.0 + 0.4999 / w_, -0.4999 / h_]
+    x["loc"] = loc
+    ref = oracle(x["value"], x["shapes"], x["lsi"], x["loc"], x["aw"], x["grad_out"])
+    h0, w0, k0 = c_oracle.sample_index(x["shapes"], x["loc"], "f32")
+    for fam in FAMILY_IDS:
+        with Paths(*FAMILIES[fam]):
+            res = run_cabi("f32", x["value"], x["shapes"], x["lsi"], x["loc"], x["aw"], x["grad_out"])
+        for key in ("out", "grad_value", "grad_loc", "grad_aw"):
+            assert np.isfinite(res[key]).all(), (fam, key)
+        check_all(res, ref)
+        assert np.all(res["grad_loc"][k0 == 0] == 0) and np.all(res["grad_aw"][k0 == 0] == 0), fam
+
+
 def test_special_locations_contribute_zero():
     wl = Workload("s", 1, ((4, 5), (2, 3)), 8, M=8, D=32, P=4, loc_dist="uniform")
     x = np_inputs(wl, 1)
