@@ -27,18 +27,23 @@ std::atomic<int> g_split_mode{0};   // 0 auto, 1 never, 2 always
 std::atomic<long long> g_launches{0};
 const char* g_last_path[2] = {"none", "none"};
 
+// SM count of the CURRENT device (one process may drive several devices; cached per device).
 int sm_count() {
-  static int cached = 0;
-  if (cached == 0) {
-    int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess ||
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) {
-      cudaGetLastError();
-      return 148;
-    }
-    cached = n;
+  static std::atomic<int> cached[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    cudaGetLastError();
+    return 148;
   }
-  return cached;
+  const int slot = dev >= 0 && dev < 64 ? dev : 0;
+  int n = cached[slot].load(std::memory_order_relaxed);
+  if (n > 0) return n;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) {
+    cudaGetLastError();
+    return 148;
+  }
+  cached[slot].store(n, std::memory_order_relaxed);
+  return n;
 }
 
 bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
@@ -480,6 +485,9 @@ struct msda_host_plan {
   cudaEvent_t* ev_run;          // [N * n_chunks] chunk results computed
   cudaEvent_t* ev_value;        // [N] value[b] on the device
   cudaEvent_t ev_tables, ev_zero;
+  cudaEvent_t* ev_out;          // [N * n_chunks + N] trace only: chunk results / grad_value[b] on the host
+  int ramp;                     // MSDA_B200_HOST_RAMP=1: growing chunks in the first sample (measured: no gain)
+  int trace;                    // MSDA_B200_HOST_TRACE=1: print the timeline of every call to stderr
 };
 
 #define MSDA_CUDA_TRY(expr)                     \
@@ -500,6 +508,7 @@ int msda_host_plan_create(msda_host_plan** out_plan, int device, int N, int S, i
     return MSDA_ERR_NO_DEVICE;
   }
   MSDA_CUDA_TRY(cudaSetDevice(device));
+  cudaGetLastError();  // a stale, non-sticky error of an earlier caller must not fail this call
   msda_host_plan* pl = new (std::nothrow) msda_host_plan();
   if (!pl) return (int)cudaErrorMemoryAllocation;
   memset(pl, 0, sizeof(*pl));
@@ -528,16 +537,24 @@ int msda_host_plan_create(msda_host_plan** out_plan, int device, int N, int S, i
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&pl->s_run, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&pl->s_out, cudaStreamNonBlocking);
   const int n_ev = (N > 0 ? N : 1) * pl->n_chunks;
+  pl->trace = getenv("MSDA_B200_HOST_TRACE") != nullptr;
+  pl->ramp = 0;
+  if (const char* env = getenv("MSDA_B200_HOST_RAMP")) pl->ramp = atoi(env) != 0;
+  const unsigned ev_flags = pl->trace ? cudaEventDefault : cudaEventDisableTiming;
+  if (pl->trace) {
+    pl->ev_out = new (std::nothrow) cudaEvent_t[n_ev + (N > 0 ? N : 1)]();
+    for (int i = 0; pl->ev_out && i < n_ev + N; ++i) cudaEventCreate(&pl->ev_out[i]);
+  }
   pl->ev_in = new (std::nothrow) cudaEvent_t[n_ev]();
   pl->ev_run = new (std::nothrow) cudaEvent_t[n_ev]();
   pl->ev_value = new (std::nothrow) cudaEvent_t[N > 0 ? N : 1]();
   if (!pl->ev_in || !pl->ev_run || !pl->ev_value) e = cudaErrorMemoryAllocation;
   for (int i = 0; i < n_ev && e == cudaSuccess; ++i) {
-    e = cudaEventCreateWithFlags(&pl->ev_in[i], cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&pl->ev_run[i], cudaEventDisableTiming);
+    e = cudaEventCreateWithFlags(&pl->ev_in[i], ev_flags);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&pl->ev_run[i], ev_flags);
   }
-  for (int i = 0; i < N && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&pl->ev_value[i], cudaEventDisableTiming);
-  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&pl->ev_tables, cudaEventDisableTiming);
+  for (int i = 0; i < N && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&pl->ev_value[i], ev_flags);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&pl->ev_tables, ev_flags);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&pl->ev_zero, cudaEventDisableTiming);
   auto alloc = [&](float** p, size_t n) {
     if (e == cudaSuccess) e = cudaMalloc((void**)p, sizeof(float) * (n ? n : 1));
@@ -573,6 +590,11 @@ void msda_host_plan_destroy(msda_host_plan* pl) {
   }
   for (int i = 0; i < pl->N; ++i)
     if (pl->ev_value && pl->ev_value[i]) cudaEventDestroy(pl->ev_value[i]);
+  if (pl->ev_out) {
+    for (int i = 0; i < n_ev + pl->N; ++i)
+      if (pl->ev_out[i]) cudaEventDestroy(pl->ev_out[i]);
+    delete[] pl->ev_out;
+  }
   delete[] pl->ev_in; delete[] pl->ev_run; delete[] pl->ev_value;
   if (pl->ev_tables) cudaEventDestroy(pl->ev_tables);
   if (pl->ev_zero) cudaEventDestroy(pl->ev_zero);
@@ -629,7 +651,13 @@ static int host_pipeline(msda_host_plan* pl, const float* value, const int64_t* 
     MSDA_CUDA_TRY(cudaEventRecord(pl->ev_value[b], pl->s_in));
     MSDA_CUDA_TRY(cudaStreamWaitEvent(pl->s_run, pl->ev_value[b], 0));
     for (int c = 0; c < pl->n_chunks; ++c) {
-      const int q0 = (int)((long long)Lq * c / pl->n_chunks), q1 = (int)((long long)Lq * (c + 1) / pl->n_chunks);
+      // equal chunks, except in the first sample where they grow quadratically: a small first chunk
+      // gets the download stream going early, large later chunks keep the copies efficient
+      auto cut = [&](int i) {
+        const long long C = pl->n_chunks;
+        return (b == 0 && pl->ramp) ? (int)((long long)Lq * i * i / (C * C)) : (int)((long long)Lq * i / C);
+      };
+      const int q0 = cut(c), q1 = cut(c + 1);
       const int nq = q1 - q0;
       const int k = b * pl->n_chunks + c;
       const size_t qo = (size_t)b * Lq + q0;
@@ -660,21 +688,46 @@ static int host_pipeline(msda_host_plan* pl, const float* value, const int64_t* 
         MSDA_CUDA_TRY(cudaMemcpyAsync(gl + qo * a_per_q * 2, pl->d_gl + qo * a_per_q * 2, sizeof(float) * nq * a_per_q * 2, D2H, pl->s_out));
         MSDA_CUDA_TRY(cudaMemcpyAsync(ga + qo * a_per_q, pl->d_ga + qo * a_per_q, sizeof(float) * nq * a_per_q, D2H, pl->s_out));
       }
+      if (pl->trace && pl->ev_out) cudaEventRecord(pl->ev_out[k], pl->s_out);
     }
     if (bwd && v_per)
       MSDA_CUDA_TRY(cudaMemcpyAsync(gv + b * v_per, pl->d_gv + b * v_per, sizeof(float) * v_per, D2H, pl->s_out));
+    if (pl->trace && pl->ev_out) cudaEventRecord(pl->ev_out[N * pl->n_chunks + b], pl->s_out);
   }
   MSDA_CUDA_TRY(cudaStreamSynchronize(pl->s_out));
   MSDA_CUDA_TRY(cudaStreamSynchronize(pl->s_run));
   MSDA_CUDA_TRY(cudaStreamSynchronize(pl->s_in));
+  if (pl->trace && pl->ev_out) {
+    auto at = [&](cudaEvent_t e) { float ms = 0.f; cudaEventElapsedTime(&ms, pl->ev_tables, e); return ms; };
+    fprintf(stderr, "[msda host trace] ms after the level tables landed:  in = chunk inputs on device, run = kernels done, out = results on host\n");
+    for (int b = 0; b < N; ++b) {
+      fprintf(stderr, "  sample %d: value in %.3f\n", b, at(pl->ev_value[b]));
+      for (int c = 0; c < pl->n_chunks; ++c) {
+        const int k = b * pl->n_chunks + c;
+        fprintf(stderr, "    chunk %d: in %.3f  run %.3f  out %.3f\n", c, at(pl->ev_in[k]), at(pl->ev_run[k]), at(pl->ev_out[k]));
+      }
+      if (bwd) fprintf(stderr, "    grad_value out %.3f\n", at(pl->ev_out[N * pl->n_chunks + b]));
+    }
+  }
   return MSDA_OK;
+}
+
+// On failure nothing may still be reading or writing the caller's buffers when we return.
+static int host_finish(msda_host_plan* pl, int rc) {
+  if (rc != MSDA_OK) {
+    cudaStreamSynchronize(pl->s_in);
+    cudaStreamSynchronize(pl->s_run);
+    cudaStreamSynchronize(pl->s_out);
+    cudaGetLastError();
+  }
+  return rc;
 }
 
 int msda_host_fwd_f32(msda_host_plan* pl, const float* value, const int64_t* shapes, const int64_t* lsi,
                       const float* loc, const float* aw, float* out) {
   if (!pl || !value || !shapes || !lsi || !loc || !aw || !out) return MSDA_ERR_NULL_POINTER;
   MSDA_CUDA_TRY(cudaSetDevice(pl->device));
-  return host_pipeline(pl, value, shapes, lsi, loc, aw, nullptr, out, nullptr, nullptr, nullptr);
+  return host_finish(pl, host_pipeline(pl, value, shapes, lsi, loc, aw, nullptr, out, nullptr, nullptr, nullptr));
 }
 
 int msda_host_fwd_bwd_f32(msda_host_plan* pl, const float* value, const int64_t* shapes,
@@ -683,7 +736,7 @@ int msda_host_fwd_bwd_f32(msda_host_plan* pl, const float* value, const int64_t*
   if (!pl || !value || !shapes || !lsi || !loc || !aw || !go || !out || !gv || !gl || !ga)
     return MSDA_ERR_NULL_POINTER;
   MSDA_CUDA_TRY(cudaSetDevice(pl->device));
-  return host_pipeline(pl, value, shapes, lsi, loc, aw, go, out, gv, gl, ga);
+  return host_finish(pl, host_pipeline(pl, value, shapes, lsi, loc, aw, go, out, gv, gl, ga));
 }
 
 }  // extern "C"
