@@ -85,6 +85,41 @@ __global__ void __launch_bounds__(256) tma_red_kernel(float* dst, unsigned span_
   if (lane < 4) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
+// Mixed: warps [0, LSU_WARPS) of every CTA reduce with red.global.add.v4.f32, the others with TMA bulk
+// reduce.  If the two paths had separate ports out of the SM their throughputs would add.
+template <int LSU_WARPS>
+__global__ void __launch_bounds__(256) mixed_red_kernel(float* dst, unsigned span_rows, int iters, unsigned seed) {
+  __shared__ __align__(128) float stage[8][2][4][32];
+  const unsigned gtid = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const unsigned warp = gtid >> 5;
+  if ((int)wib < LSU_WARPS) {
+    for (int i = 0; i < iters; ++i) {
+      const unsigned row = hash32(seed + (warp * iters + i) * 4 + (lane >> 3)) % span_rows;
+      asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(dst + (size_t)row * 32 + (lane & 7) * 4), "f"(1.f), "f"(1.f), "f"(1.f), "f"(1.f) : "memory");
+    }
+    return;
+  }
+  for (int i = 0; i < iters; ++i) {
+    const int buf = i & 1;
+    if (lane < 4) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+    __syncwarp();
+    float4* s = reinterpret_cast<float4*>(&stage[wib][buf][lane >> 3][(lane & 7) * 4]);
+    *s = make_float4(1.f, 1.f, 1.f, 1.f);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane < 4) {
+      const unsigned row = hash32(seed + (warp * iters + i) * 4 + lane) % span_rows;
+      const unsigned saddr = (unsigned)__cvta_generic_to_shared(&stage[wib][buf][lane][0]);
+      asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(dst + (size_t)row * 32),
+                   "r"(saddr), "n"(128)
+                   : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+  }
+  if (lane < 4) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 int main(int argc, char** argv) {
   const unsigned span_rows = argc > 1 ? (unsigned)atoi(argv[1]) : 355568u;  // 45.5 MB of 128 B rows
   const int total_rows = 22757376;                                         // C2 backward: samples * 4 corners
@@ -132,6 +167,22 @@ int main(int argc, char** argv) {
       if (ms < best) best = ms;
     }
     printf("%-36s %8.1f us   %7.2f TB/s payload\n", "cp.reduce.async.bulk 128 B/op", best * 1e3, bytes / (best * 1e-3) / 1e12);
+  }
+  for (int split = 0; split < 3; ++split) {
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {
+      CK(cudaEventRecord(e0));
+      if (split == 0) mixed_red_kernel<4><<<ctas, threads>>>(dst, span_rows, per_group, rep * 7919u);
+      if (split == 1) mixed_red_kernel<5><<<ctas, threads>>>(dst, span_rows, per_group, rep * 7919u);
+      if (split == 2) mixed_red_kernel<6><<<ctas, threads>>>(dst, span_rows, per_group, rep * 7919u);
+      CK(cudaEventRecord(e1));
+      CK(cudaEventSynchronize(e1));
+      float ms;
+      CK(cudaEventElapsedTime(&ms, e0, e1));
+      if (ms < best) best = ms;
+    }
+    printf("mixed: %d of 8 warps red.v4, rest TMA      %8.1f us   %7.2f TB/s payload\n", 4 + split, best * 1e3,
+           bytes / (best * 1e-3) / 1e12);
   }
   CK(cudaDeviceSynchronize());
   printf("done\n");
