@@ -129,7 +129,7 @@ int launch_fwd_d32(D32Params& p, cudaStream_t st, bool* split = nullptr) {
     fwd_d32_split_kernel<VT, kFuse><<<split_grid(p.n_items, 4), kD32Threads, kSplitSmem, st>>>(p);
     return finish_launch(1);
   }
-  const int grid = d32_grid(p.n_items, MSDA_FWD_MINB, MSDA_FWD_WAVES);
+  const int grid = d32_grid(p.n_items, MSDA_FWD_MINB, sizeof(VT) == 4 ? MSDA_FWD_WAVES : MSDA_FWD_WAVES_BF16);
   if (p.L == 4 && p.P == 4 && p.M == 8) {   // the shipped geometry (util/settings.py:102-120)
     fwd_d32_kernel<VT, 4, 4, 8, kFuse><<<grid, kD32Threads, d32_smem(LP), st>>>(p);
   } else {

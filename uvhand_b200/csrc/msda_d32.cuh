@@ -57,6 +57,14 @@ namespace msda {
 #ifndef MSDA_FWD_WAVES
 #define MSDA_FWD_WAVES 1
 #endif
+// bf16 values: rows are half as long, the gathers finish sooner and the forward prefers short-lived
+// CTAs without the pipelined phase A (C2 bf16: 150 -> 135 us)
+#ifndef MSDA_FWD_PREFETCH_BF16
+#define MSDA_FWD_PREFETCH_BF16 0
+#endif
+#ifndef MSDA_FWD_WAVES_BF16
+#define MSDA_FWD_WAVES_BF16 2
+#endif
 #ifndef MSDA_BWD_WAVES
 #define MSDA_BWD_WAVES 11
 #endif
@@ -302,7 +310,8 @@ fwd_d32_kernel(const D32Params p) {
 
   const long long n_pass = (p.n_items + kItemsPerWarp - 1) / kItemsPerWarp;
   const long long pass_stride = (long long)gridDim.x * kD32Warps;
-  constexpr bool kPipe = kStatic && MSDA_FWD_PREFETCH && (kItemsPerWarp * kL * kP) % kWarp == 0 &&
+  constexpr bool kPrefetch = sizeof(typename C::Vec) == 16 ? MSDA_FWD_PREFETCH : MSDA_FWD_PREFETCH_BF16;
+  constexpr bool kPipe = kStatic && kPrefetch && (kItemsPerWarp * kL * kP) % kWarp == 0 &&
                          (!kFuse || ((kL * kP) & (kL * kP - 1)) == 0);
   RawSamples<kPipe ? kL * kP : kWarp> raw;
   const long long pass0 = (long long)blockIdx.x * kD32Warps + warp;
