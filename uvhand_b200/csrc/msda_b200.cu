@@ -626,6 +626,15 @@ int msda_host_unregister(void* ptr) {
   return MSDA_OK;
 }
 
+// The (up to three) copies of one chunk, issued back to back on one stream.
+static cudaError_t copy_batch(void** dsts, void** srcs, size_t* sizes, int n, cudaMemcpyKind kind, cudaStream_t st) {
+  for (int i = 0; i < n; ++i) {
+    const cudaError_t e = cudaMemcpyAsync(dsts[i], srcs[i], sizes[i], kind, st);
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
+
 // One call = N * n_chunks work packets (sample b, queries [q0, q1)):
 //   s_in : tables, then per sample: value[b], then per chunk: loc, aw (, grad_out)
 //   s_run: memset(grad_value); per chunk: forward (+ backward) on that query range of sample b
@@ -661,12 +670,17 @@ static int host_pipeline(msda_host_plan* pl, const float* value, const int64_t* 
       const int nq = q1 - q0;
       const int k = b * pl->n_chunks + c;
       const size_t qo = (size_t)b * Lq + q0;
-      if (nq > 0 && a_per_q) {
-        MSDA_CUDA_TRY(cudaMemcpyAsync(pl->d_loc + qo * a_per_q * 2, loc + qo * a_per_q * 2, sizeof(float) * nq * a_per_q * 2, H2D, pl->s_in));
-        MSDA_CUDA_TRY(cudaMemcpyAsync(pl->d_aw + qo * a_per_q, aw + qo * a_per_q, sizeof(float) * nq * a_per_q, H2D, pl->s_in));
+      {
+        void* dsts[3]; void* srcs[3]; size_t sizes[3]; int n = 0;
+        if (nq > 0 && a_per_q) {
+          dsts[n] = pl->d_loc + qo * a_per_q * 2; srcs[n] = const_cast<float*>(loc + qo * a_per_q * 2); sizes[n++] = sizeof(float) * nq * a_per_q * 2;
+          dsts[n] = pl->d_aw + qo * a_per_q; srcs[n] = const_cast<float*>(aw + qo * a_per_q); sizes[n++] = sizeof(float) * nq * a_per_q;
+        }
+        if (bwd && nq > 0 && o_per_q) {
+          dsts[n] = pl->d_go + qo * o_per_q; srcs[n] = const_cast<float*>(go + qo * o_per_q); sizes[n++] = sizeof(float) * nq * o_per_q;
+        }
+        if (n) MSDA_CUDA_TRY(copy_batch(dsts, srcs, sizes, n, H2D, pl->s_in));
       }
-      if (bwd && nq > 0 && o_per_q)
-        MSDA_CUDA_TRY(cudaMemcpyAsync(pl->d_go + qo * o_per_q, go + qo * o_per_q, sizeof(float) * nq * o_per_q, H2D, pl->s_in));
       MSDA_CUDA_TRY(cudaEventRecord(pl->ev_in[k], pl->s_in));
       MSDA_CUDA_TRY(cudaStreamWaitEvent(pl->s_run, pl->ev_in[k], 0));
       if (nq > 0) {
@@ -682,11 +696,16 @@ static int host_pipeline(msda_host_plan* pl, const float* value, const int64_t* 
       }
       MSDA_CUDA_TRY(cudaEventRecord(pl->ev_run[k], pl->s_run));
       MSDA_CUDA_TRY(cudaStreamWaitEvent(pl->s_out, pl->ev_run[k], 0));
-      if (nq > 0 && o_per_q)
-        MSDA_CUDA_TRY(cudaMemcpyAsync(out + qo * o_per_q, pl->d_out + qo * o_per_q, sizeof(float) * nq * o_per_q, D2H, pl->s_out));
-      if (bwd && nq > 0 && a_per_q) {
-        MSDA_CUDA_TRY(cudaMemcpyAsync(gl + qo * a_per_q * 2, pl->d_gl + qo * a_per_q * 2, sizeof(float) * nq * a_per_q * 2, D2H, pl->s_out));
-        MSDA_CUDA_TRY(cudaMemcpyAsync(ga + qo * a_per_q, pl->d_ga + qo * a_per_q, sizeof(float) * nq * a_per_q, D2H, pl->s_out));
+      {
+        void* dsts[3]; void* srcs[3]; size_t sizes[3]; int n = 0;
+        if (nq > 0 && o_per_q) {
+          dsts[n] = out + qo * o_per_q; srcs[n] = pl->d_out + qo * o_per_q; sizes[n++] = sizeof(float) * nq * o_per_q;
+        }
+        if (bwd && nq > 0 && a_per_q) {
+          dsts[n] = gl + qo * a_per_q * 2; srcs[n] = pl->d_gl + qo * a_per_q * 2; sizes[n++] = sizeof(float) * nq * a_per_q * 2;
+          dsts[n] = ga + qo * a_per_q; srcs[n] = pl->d_ga + qo * a_per_q; sizes[n++] = sizeof(float) * nq * a_per_q;
+        }
+        if (n) MSDA_CUDA_TRY(copy_batch(dsts, srcs, sizes, n, D2H, pl->s_out));
       }
       if (pl->trace && pl->ev_out) cudaEventRecord(pl->ev_out[k], pl->s_out);
     }
