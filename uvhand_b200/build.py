@@ -68,6 +68,20 @@ def build_cabi(force: bool = False, verbose: bool = True) -> str:
     return CABI_SO
 
 
+CHECKED_SO = os.path.join(LIBDIR, "libmsda_b200_checked.so")
+
+
+def build_checked(force: bool = False, verbose: bool = True) -> str:
+    """The same library with -DMSDA_BOUNDS_CHECK=1: every data-dependent gather / reduction address is
+    compared with the tensor's extent inside the kernels (tests run the parity suite through it; it is
+    never loaded by the product path -- select it with MSDA_B200_LIB)."""
+    os.makedirs(LIBDIR, exist_ok=True)
+    if force or _stale(CHECKED_SO, cabi_sources()):
+        _run([_nvcc(), *NVCC_ARCH, "-O3", "-std=c++17", "-lineinfo", "-shared", "-Xcompiler", "-fPIC", "-ccbin", _cxx(),
+              "-DMSDA_BOUNDS_CHECK=1", "-o", CHECKED_SO, os.path.join(CSRC, "msda_b200.cu")], verbose)
+    return CHECKED_SO
+
+
 def build_torch_ext(force: bool = False, verbose: bool = True) -> str:
     build_cabi(force, verbose)
     src = os.path.join(CSRC, "msda_torch.cpp")
@@ -91,6 +105,7 @@ def build_torch_ext(force: bool = False, verbose: bool = True) -> str:
 
 
 def build_all(force: bool = False, verbose: bool = True):
+    build_checked(force, verbose)
     return build_cabi(force, verbose), build_torch_ext(force, verbose)
 
 

@@ -61,6 +61,20 @@ int check_dims(int N, int S, int M, int D, int L, int Lq, int P) {
 
 bool nothing_to_do(int N, int M, int D, int Lq) { return N == 0 || M == 0 || D == 0 || Lq == 0; }
 
+// Checked build only: tell the kernels the extent of value / grad_value for the launch that follows
+// (debug facility: one launch at a time per process).
+void register_extents(const void* value, size_t value_bytes, const void* gv, size_t gv_bytes, cudaStream_t st) {
+#if MSDA_BOUNDS_CHECK
+  const char* lo[2] = {(const char*)value, (const char*)gv};
+  const char* hi[2] = {(const char*)value + value_bytes, (const char*)gv + gv_bytes};
+  cudaStreamSynchronize(st);
+  cudaMemcpyToSymbol(g_chk_lo, lo, sizeof(lo));
+  cudaMemcpyToSymbol(g_chk_hi, hi, sizeof(hi));
+#else
+  (void)value; (void)value_bytes; (void)gv; (void)gv_bytes; (void)st;
+#endif
+}
+
 int finish_launch(int n_launched) {
   g_launches.fetch_add(n_launched, std::memory_order_relaxed);
   const cudaError_t e = cudaGetLastError();
@@ -125,6 +139,7 @@ int launch_fwd_d32(D32Params& p, cudaStream_t st, bool* split = nullptr) {
   p.n_items = (long long)p.N * p.Lq * p.M;
   const bool sp = use_split(p.n_items, MSDA_FWD_MINB, false);
   if (split) *split = sp;
+  register_extents(p.value, (size_t)p.N * p.S * p.M * 32 * sizeof(VT), nullptr, 0, st);
   if (sp) {
     fwd_d32_split_kernel<VT, kFuse><<<split_grid(p.n_items, 4), kD32Threads, kSplitSmem, st>>>(p);
     return finish_launch(1);
@@ -144,6 +159,8 @@ int launch_bwd_d32(D32Params& p, cudaStream_t st, bool* split = nullptr) {
   p.n_items = (long long)p.N * p.Lq * p.M;
   const bool sp = !kFuse && use_split(p.n_items, MSDA_BWD_MINB, true);
   if (split) *split = sp;
+  register_extents(p.value, (size_t)p.N * p.S * p.M * 32 * sizeof(VT), p.grad_value,
+                   (size_t)p.N * p.S * p.M * 32 * sizeof(GT), st);
   if (sp) {
     bwd_d32_split_kernel<VT, GT><<<split_grid(p.n_items, 3), kD32Threads, kSplitSmem, st>>>(p);
     return finish_launch(1);
@@ -162,6 +179,7 @@ int fwd_any(const T* value, const int64_t* shapes, const int64_t* lsi, const T* 
             int N, int S, int M, int D, int L, int Lq, int P, T* out, cudaStream_t st) {
   const Dims d{N, S, M, D, L, Lq, P};
   const long long n_items = (long long)N * Lq * M;
+  register_extents(value, (size_t)N * S * M * D * sizeof(T), nullptr, 0, st);
   fwd_generic_kernel<T><<<generic_grid(n_items), kGenericThreads, 0, st>>>(value, shapes, lsi, loc, aw, d, out);
   return finish_launch(1);
 }
@@ -172,6 +190,7 @@ int bwd_any(const T* go, const T* value, const int64_t* shapes, const int64_t* l
             cudaStream_t st) {
   const Dims d{N, S, M, D, L, Lq, P};
   const long long n_items = (long long)N * Lq * M;
+  register_extents(value, (size_t)N * S * M * D * sizeof(T), gv, (size_t)N * S * M * D * sizeof(T), st);
   bwd_generic_kernel<T><<<generic_grid(n_items), kGenericThreads, 0, st>>>(go, value, shapes, lsi, loc, aw, d, gv, gl, ga);
   return finish_launch(1);
 }

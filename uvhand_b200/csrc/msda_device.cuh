@@ -12,6 +12,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 
 namespace msda {
 
@@ -60,6 +61,30 @@ __device__ __forceinline__ bool sample_geom(T loc_x, T loc_y, int H, int W, Samp
   return true;
 }
 
+// ---- optional bounds checking (-DMSDA_BOUNDS_CHECK=1: the "checked" library the tests also run) ----
+// compute-sanitizer is not available on the GPU pool this was developed on, so the kernels carry
+// their own memcheck for the accesses whose addresses depend on DATA (sampling locations): every
+// gathered value row and every grad_value reduction is compared with the extent of the tensor the
+// host registered for this launch; a violation prints once and traps (the launch fails).
+#ifndef MSDA_BOUNDS_CHECK
+#define MSDA_BOUNDS_CHECK 0
+#endif
+#if MSDA_BOUNDS_CHECK
+__device__ const char* g_chk_lo[2];   // [0] value, [1] grad_value (or its fp32 scratch)
+__device__ const char* g_chk_hi[2];
+__device__ __forceinline__ void chk_access(const void* p, unsigned bytes, int which) {
+  const char* c = reinterpret_cast<const char*>(p);
+  if (c < g_chk_lo[which] || c + bytes > g_chk_hi[which]) {
+    printf("msda bounds check: %s access of %u B at %p outside [%p, %p)\n", which ? "grad_value" : "value", bytes, p,
+           (const void*)g_chk_lo[which], (const void*)g_chk_hi[which]);
+    __trap();
+  }
+}
+#define MSDA_CHK(p, bytes, which) chk_access((p), (bytes), (which))
+#else
+#define MSDA_CHK(p, bytes, which) ((void)0)
+#endif
+
 // ---- memory helpers ---------------------------------------------------------------------
 
 // Streaming (read-once) inputs: do not let them evict gathered value rows from L1.
@@ -99,9 +124,13 @@ struct Chunk;
 template <>
 struct Chunk<float> {
   using Vec = float4;
-  static __device__ __forceinline__ float4 load(const Vec* p) { return __ldg(p); }
+  static __device__ __forceinline__ float4 load(const Vec* p) {
+    MSDA_CHK(p, 16, 0);
+    return __ldg(p);
+  }
   // red.global.add.v4.f32: one 16 B reduction instead of four scalar atomics (sm_90+).
   static __device__ __forceinline__ void red_add(Vec* p, float4 v) {
+    MSDA_CHK(p, 16, 1);
     asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
                  "f"(v.w)
                  : "memory");
@@ -111,6 +140,7 @@ template <>
 struct Chunk<__nv_bfloat16> {
   using Vec = uint2;
   static __device__ __forceinline__ float4 load(const Vec* p) {
+    MSDA_CHK(p, 8, 0);
     const uint2 r = __ldg(p);
     float4 v;
     v.x = __uint_as_float(r.x << 16);
@@ -120,6 +150,7 @@ struct Chunk<__nv_bfloat16> {
     return v;
   }
   static __device__ __forceinline__ void red_add(Vec* p, float4 v) {
+    MSDA_CHK(p, 8, 1);
     const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y);
     const __nv_bfloat162 hi = __floats2bfloat162_rn(v.z, v.w);
     const unsigned a = *reinterpret_cast<const unsigned*>(&lo);

@@ -54,6 +54,10 @@ fwd_generic_kernel(const T* __restrict__ value, const int64_t* __restrict__ shap
           if (!live) continue;
           const T hh = 1 - g.lh, hw = 1 - g.lw;
           const long long r00 = ((long long)g.h_low * W + g.w_low) * row_stride + c;
+          if (g.mask & 1u) MSDA_CHK(vl + r00, sizeof(T), 0);
+          if (g.mask & 2u) MSDA_CHK(vl + r00 + row_stride, sizeof(T), 0);
+          if (g.mask & 4u) MSDA_CHK(vl + r00 + (long long)W * row_stride, sizeof(T), 0);
+          if (g.mask & 8u) MSDA_CHK(vl + r00 + (long long)(W + 1) * row_stride, sizeof(T), 0);
           const T v1 = (g.mask & 1u) ? vl[r00] : (T)0;
           const T v2 = (g.mask & 2u) ? vl[r00 + row_stride] : (T)0;
           const T v3 = (g.mask & 4u) ? vl[r00 + (long long)W * row_stride] : (T)0;
@@ -112,10 +116,10 @@ bwd_generic_kernel(const T* __restrict__ grad_out, const T* __restrict__ value,
             const T top = g_row[c];
             const T t = top * a;
             T v1 = 0, v2 = 0, v3 = 0, v4 = 0;
-            if (g.mask & 1u) { v1 = value[r00 + c]; atomicAdd(grad_value + r00 + c, w1 * t); }
-            if (g.mask & 2u) { v2 = value[r01 + c]; atomicAdd(grad_value + r01 + c, w2 * t); }
-            if (g.mask & 4u) { v3 = value[r10 + c]; atomicAdd(grad_value + r10 + c, w3 * t); }
-            if (g.mask & 8u) { v4 = value[r11 + c]; atomicAdd(grad_value + r11 + c, w4 * t); }
+            if (g.mask & 1u) { MSDA_CHK(value + r00 + c, sizeof(T), 0); MSDA_CHK(grad_value + r00 + c, sizeof(T), 1); v1 = value[r00 + c]; atomicAdd(grad_value + r00 + c, w1 * t); }
+            if (g.mask & 2u) { MSDA_CHK(value + r01 + c, sizeof(T), 0); MSDA_CHK(grad_value + r01 + c, sizeof(T), 1); v2 = value[r01 + c]; atomicAdd(grad_value + r01 + c, w2 * t); }
+            if (g.mask & 4u) { MSDA_CHK(value + r10 + c, sizeof(T), 0); MSDA_CHK(grad_value + r10 + c, sizeof(T), 1); v3 = value[r10 + c]; atomicAdd(grad_value + r10 + c, w3 * t); }
+            if (g.mask & 8u) { MSDA_CHK(value + r11 + c, sizeof(T), 0); MSDA_CHK(grad_value + r11 + c, sizeof(T), 1); v4 = value[r11 + c]; atomicAdd(grad_value + r11 + c, w4 * t); }
             const T gh = hw * (v3 - v1) + g.lw * (v4 - v2);
             const T gw = hh * (v2 - v1) + g.lh * (v4 - v3);
             ga += top * (w1 * v1 + w2 * v2 + w3 * v3 + w4 * v4);
