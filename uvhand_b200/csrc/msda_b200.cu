@@ -147,6 +147,8 @@ int launch_fwd_d32(D32Params& p, cudaStream_t st, bool* split = nullptr) {
   const int grid = d32_grid(p.n_items, MSDA_FWD_MINB, sizeof(VT) == 4 ? MSDA_FWD_WAVES : MSDA_FWD_WAVES_BF16);
   if (p.L == 4 && p.P == 4 && p.M == 8) {   // the shipped geometry (util/settings.py:102-120)
     fwd_d32_kernel<VT, 4, 4, 8, kFuse><<<grid, kD32Threads, d32_smem(LP), st>>>(p);
+  } else if (p.L == 4 && p.P == 4) {        // same sampling pattern, another head count
+    fwd_d32_kernel<VT, 4, 4, 0, kFuse><<<grid, kD32Threads, d32_smem(LP), st>>>(p);
   } else {
     fwd_d32_kernel<VT, 0, 0, 0, kFuse><<<grid, kD32Threads, d32_smem(LP), st>>>(p);
   }
@@ -168,6 +170,8 @@ int launch_bwd_d32(D32Params& p, cudaStream_t st, bool* split = nullptr) {
   const int grid = d32_grid(p.n_items, MSDA_BWD_MINB, MSDA_BWD_WAVES);
   if (p.L == 4 && p.P == 4 && p.M == 8) {
     bwd_d32_kernel<VT, GT, 4, 4, 8, kFuse><<<grid, kD32Threads, d32_smem(LP), st>>>(p);
+  } else if (p.L == 4 && p.P == 4) {
+    bwd_d32_kernel<VT, GT, 4, 4, 0, kFuse><<<grid, kD32Threads, d32_smem(LP), st>>>(p);
   } else {
     bwd_d32_kernel<VT, GT, 0, 0, 0, kFuse><<<grid, kD32Threads, d32_smem(LP), st>>>(p);
   }
