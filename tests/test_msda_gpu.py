@@ -41,24 +41,27 @@ def dev(a, dtype=None):
 
 class Paths:
     """Context manager forcing a kernel family.  fwd/bwd: 0 auto, 1 any-shape kernels;
-    split: 0 auto (by problem size), 1 never (4 items per warp), 2 always (1 item per warp)."""
+    split: 0 auto (by problem size), 1 never (4 items per warp), 2 always (1 item per warp);
+    maps: 2 = the experimental backward with on-chip maps of the coarse levels (L = P = 4), else never."""
 
-    def __init__(self, fwd=0, bwd=0, split=0):
-        self.f, self.b, self.s = fwd, bwd, split
+    def __init__(self, fwd=0, bwd=0, split=0, maps=1):
+        self.f, self.b, self.s, self.m = fwd, bwd, split, maps
 
     def __enter__(self):
         cabi.set_option("fwd_path", self.f)
         cabi.set_option("bwd_path", self.b)
         cabi.set_option("split_mode", self.s)
+        cabi.set_option("bwd_maps", self.m)
 
     def __exit__(self, *a):
         cabi.set_option("fwd_path", 0)
         cabi.set_option("bwd_path", 0)
         cabi.set_option("split_mode", 0)
+        cabi.set_option("bwd_maps", 0)
 
 
-# the three kernel families every parity case runs through (D = 32 shapes)
-FAMILIES = {"d32": (0, 0, 1), "split": (0, 0, 2), "anyshape": (1, 1, 0)}
+# the kernel families every parity case runs through (D = 32 shapes; "maps" applies to L = P = 4 only)
+FAMILIES = {"d32": (0, 0, 1, 1), "split": (0, 0, 2, 1), "maps": (0, 0, 1, 2), "anyshape": (1, 1, 0, 1)}
 FAMILY_IDS = list(FAMILIES)
 
 
@@ -125,7 +128,9 @@ def test_golden_f32(path, forced):
         res = run_cabi("f32", g["value"], g["shapes"], g["lsi"], g["loc"], g["aw"], g["grad_out"])
     check_all(res, g)
     if g["value"].shape[3] == 32:
+        l4p4 = g["loc"].shape[3] == 4 and g["loc"].shape[4] == 4
         want = {"d32": ("fwd_d32_f32", "bwd_d32_f32"), "split": ("fwd_d32_split_f32", "bwd_d32_split_f32"),
+                "maps": ("fwd_d32_f32", "bwd_d32_maps_f32" if l4p4 else "bwd_d32_f32"),
                 "anyshape": ("fwd_generic_f32", "bwd_generic_f32")}[forced]
         assert (res["fwd_path"], res["bwd_path"]) == want
 
@@ -282,15 +287,16 @@ SHAPES = [
 
 
 @pytest.mark.parametrize("shape", SHAPES, ids=[f"N{s[0]}M{s[1]}D{s[2]}L{s[3]}P{s[4]}Lq{s[5]}" for s in SHAPES])
-@pytest.mark.parametrize("kind", ["f32", "f32-split", "f64"])
+@pytest.mark.parametrize("kind", ["f32", "f32-split", "f32-maps", "f64"])
 def test_shape_sweep(shape, kind):
     N, M, D, L, P, Lq, levels = shape
     wl = Workload("s", N, levels, Lq, M=M, D=D, P=P, loc_dist="twostage")
     x = np_inputs(wl, 9, pad_frac=0.0, offset_px=1.0)
     x["loc"] = (x["loc"] * 0.4 + 0.5).astype(np.float32)   # mostly inside, some out
     split = 2 if kind == "f32-split" else 1                # 4-items-per-warp vs 1-item-per-warp kernels
+    maps = 2 if kind == "f32-maps" else 1                  # backward with on-chip maps (only L = P = 4 takes it)
     kind = kind.split("-")[0]
-    with Paths(0, 0, split):
+    with Paths(0, 0, split, maps):
         res = run_cabi(kind, x["value"], x["shapes"], x["lsi"], x["loc"], x["aw"], x["grad_out"])
     variant = "f32x" if kind == "f32" else "f64"
     ref = oracle(x["value"], x["shapes"], x["lsi"], x["loc"], x["aw"], x["grad_out"], variant)
@@ -470,7 +476,7 @@ def test_arctic_eval_batch_of_2048_frames_equals_the_reference_chunk_loop():
     gv_c = torch.zeros_like(gv)
     step = 64
     assert cabi.lib().msda_b200_check_im2col_step(N, step) == 0
-    with Paths(0, 0, 1):       # chunks of 64 are small enough to pick the split forward; keep the kernels identical
+    with Paths(0, 0, 1, 0):    # chunks of 64 are small enough to pick the split forward; keep the kernels identical
         for b0 in range(0, N, step):
             sl = slice(b0, b0 + step)
             dims = (step, S, M, D, L, Lq, P)

@@ -1,6 +1,6 @@
 #!/bin/bash
 # Build experimental variants of libmsda_b200.so (same ABI) into uvhand_b200/lib/variants/ for A/B timing:
-#   tools/build_variants.sh name "-DMSDA_FWD_WARPS=8 -DMSDA_FWD_MINB=5" [name2 "flags2" ...]
+#   tools/build_variants.sh name "-DMSDA_FWD_MINB=5 -DMSDA_BWD_WAVES=4" [name2 "flags2" ...]
 # then  MSDA_B200_LIB=uvhand_b200/lib/variants/name.so python tools/quick_bench.py
 set -e
 cd "$(dirname "$0")/.."

@@ -14,6 +14,7 @@
 #include <new>
 
 #include "msda_d32.cuh"
+#include "msda_d32_maps.cuh"
 #include "msda_generic.cuh"
 
 namespace {
@@ -24,6 +25,7 @@ std::atomic<int> g_fwd_path{0};
 std::atomic<int> g_bwd_path{0};
 std::atomic<int> g_bf16_direct{0};
 std::atomic<int> g_split_mode{0};   // 0 auto, 1 never, 2 always
+std::atomic<int> g_bwd_maps{0};     // 2 = use the on-chip-maps backward experiment (L = P = 4); otherwise never
 std::atomic<long long> g_launches{0};
 const char* g_last_path[2] = {"none", "none"};
 
@@ -178,6 +180,33 @@ int launch_bwd_d32(D32Params& p, cudaStream_t st, bool* split = nullptr) {
   return finish_launch(1);
 }
 
+// EXPERIMENT, never chosen automatically (option "bwd_maps" = 2 selects it): fp32 backward with the coarse
+// levels of a small pyramid accumulated in warp-private shared-memory maps (msda_d32_maps.cuh).  Measured
+// at the ARCTIC shape it LOSES to the plain kernel (encoder 402 vs 306 us, decoder 125 vs 70 us) although
+// it halves the reductions sent to L2: profiles/r01_tuning_matrix.md.  Kept as the worked example behind
+// DESIGN.md 3.3's statement about on-chip combining, and tested like every other kernel family.
+bool use_maps(const D32Params& p) {
+  return g_bwd_maps.load() == 2 && p.L == 4 && p.P == 4;
+}
+
+int launch_bwd_maps(D32Params& p, cudaStream_t st) {
+  const size_t smem = maps_smem_bytes(p.L * p.P);
+  auto go = [&](auto kernel) {
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    long long warps_needed = ((long long)p.N * p.M * p.Lq + 15) / 16;   // at least ~4 passes per warp
+    long long ctas = (warps_needed + kD32Warps - 1) / kD32Warps;
+    const long long cap = (long long)sm_count() * kMapsCtasPerSm;
+    if (ctas > cap) ctas = cap;
+    if (ctas < 1) ctas = 1;
+    register_extents(p.value, (size_t)p.N * p.S * p.M * 32 * sizeof(float), p.grad_value,
+                     (size_t)p.N * p.S * p.M * 32 * sizeof(float), st);
+    kernel<<<(int)ctas, kD32Threads, smem, st>>>(p);
+  };
+  if (p.M == 8) go(bwd_d32_maps_kernel<4, 4, 8>);
+  else go(bwd_d32_maps_kernel<4, 4, 0>);
+  return finish_launch(1);
+}
+
 template <typename T>
 int fwd_any(const T* value, const int64_t* shapes, const int64_t* lsi, const T* loc, const T* aw,
             int N, int S, int M, int D, int L, int Lq, int P, T* out, cudaStream_t st) {
@@ -250,6 +279,11 @@ int msda_b200_set_option(const char* key, int value) {
     g_split_mode.store(value);
     return MSDA_OK;
   }
+  if (!strcmp(key, "bwd_maps")) {
+    if (value < 0 || value > 2) return MSDA_ERR_BAD_OPTION;
+    g_bwd_maps.store(value);
+    return MSDA_OK;
+  }
   return MSDA_ERR_BAD_OPTION;
 }
 
@@ -259,6 +293,7 @@ int msda_b200_get_option(const char* key, int* value) {
   if (!strcmp(key, "bwd_path")) { *value = g_bwd_path.load(); return MSDA_OK; }
   if (!strcmp(key, "bf16_direct_red")) { *value = g_bf16_direct.load(); return MSDA_OK; }
   if (!strcmp(key, "split_mode")) { *value = g_split_mode.load(); return MSDA_OK; }
+  if (!strcmp(key, "bwd_maps")) { *value = g_bwd_maps.load(); return MSDA_OK; }
   return MSDA_ERR_BAD_OPTION;
 }
 
@@ -367,6 +402,10 @@ int msda_bwd_f32(const float* go, const float* value, const int64_t* shapes, con
     p.value = value; p.shapes = shapes; p.lsi = lsi; p.loc = loc; p.aw = aw; p.grad_out = go;
     p.grad_value = gv; p.grad_loc = gl; p.grad_aw = ga;
     p.N = N; p.S = S; p.M = M; p.L = L; p.Lq = Lq; p.P = P;
+    if (use_maps(p)) {
+      g_last_path[1] = "bwd_d32_maps_f32";
+      return launch_bwd_maps(p, st);
+    }
     bool sp = false;
     rc = launch_bwd_d32<float, float>(p, st, &sp);
     g_last_path[1] = sp ? "bwd_d32_split_f32" : "bwd_d32_f32";
@@ -507,7 +546,7 @@ struct msda_host_plan {
   cudaEvent_t* ev_in;           // [N * n_chunks] chunk inputs on the device
   cudaEvent_t* ev_run;          // [N * n_chunks] chunk results computed
   cudaEvent_t* ev_value;        // [N] value[b] on the device
-  cudaEvent_t ev_tables, ev_zero;
+  cudaEvent_t ev_tables;
   cudaEvent_t* ev_out;          // [N * n_chunks + N] trace only: chunk results / grad_value[b] on the host
   int ramp;                     // MSDA_B200_HOST_RAMP=1: growing chunks in the first sample (measured: no gain)
   int trace;                    // MSDA_B200_HOST_TRACE=1: print the timeline of every call to stderr
@@ -578,7 +617,6 @@ int msda_host_plan_create(msda_host_plan** out_plan, int device, int N, int S, i
   }
   for (int i = 0; i < N && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&pl->ev_value[i], ev_flags);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&pl->ev_tables, ev_flags);
-  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&pl->ev_zero, cudaEventDisableTiming);
   auto alloc = [&](float** p, size_t n) {
     if (e == cudaSuccess) e = cudaMalloc((void**)p, sizeof(float) * (n ? n : 1));
   };
@@ -620,7 +658,6 @@ void msda_host_plan_destroy(msda_host_plan* pl) {
   }
   delete[] pl->ev_in; delete[] pl->ev_run; delete[] pl->ev_value;
   if (pl->ev_tables) cudaEventDestroy(pl->ev_tables);
-  if (pl->ev_zero) cudaEventDestroy(pl->ev_zero);
   if (pl->s_in) cudaStreamDestroy(pl->s_in);
   if (pl->s_run) cudaStreamDestroy(pl->s_run);
   if (pl->s_out) cudaStreamDestroy(pl->s_out);

@@ -8,7 +8,8 @@
 //     and one red.global.add.v4.f32 per lane replaces four scalar atomics in the backward.
 //   * a warp therefore works on 4 consecutive items (same query, 4 neighbouring heads when
 //     M % 4 == 0), whose sampling locations / weights / outputs are contiguous in memory:
-//     every streaming access of the warp is one fully coalesced segment.
+//     every streaming access of the warp is one fully coalesced segment, and the four rows a
+//     gather instruction fetches are one contiguous 512 B piece of `value`.
 //
 // Two phases per warp pass, separated only by __syncwarp (no block barrier in the loop):
 //   A  "geometry": the 4*L*P samples of the pass are spread over the 32 lanes (one thread per
@@ -45,9 +46,8 @@ namespace msda {
 // (gpurun_out A/B logs summarised in profiles/r01_tuning_matrix.md):
 //   *_PREFETCH  software-pipelined phase A (next pass's locations/weights requested before the gathers)
 //   *_WAVES     grid cap in units of "CTAs the device holds at once": 1 = persistent grid
-//   FWD_PREDFMA forward corner loads and their FMAs share one predicate (no zero-fill of landing regs)
-//   BWD_PRED    same idea for the backward (load + dot + red under one predicate)
-//   STATIC_M    M = 8 compiled in: the x+1 corner becomes an immediate offset of the x corner's address
+// Tried and not kept (same file): backward load + dot + red under one predicate, backward prefetch,
+// persistent backward grid, 48 / 80 registers -- see the tuning matrix.
 #ifndef MSDA_FWD_PREFETCH
 #define MSDA_FWD_PREFETCH 1
 #endif
@@ -67,15 +67,6 @@ namespace msda {
 #endif
 #ifndef MSDA_BWD_WAVES
 #define MSDA_BWD_WAVES 11
-#endif
-#ifndef MSDA_FWD_PREDFMA
-#define MSDA_FWD_PREDFMA 1
-#endif
-#ifndef MSDA_BWD_PRED
-#define MSDA_BWD_PRED 0
-#endif
-#ifndef MSDA_STATIC_M
-#define MSDA_STATIC_M 1
 #endif
 
 constexpr int kD32Warps = 8;                  // warps per CTA
@@ -304,7 +295,7 @@ fwd_d32_kernel(const D32Params p) {
   const int group = lane >> 3, sub = lane & 7;
   int4* warp_recs = reinterpret_cast<int4*>(smem_raw) + warp * (kItemsPerWarp * stride);
   const int4* my_recs = warp_recs + group * stride;
-  const int M = (MSDA_STATIC_M && kM > 0) ? kM : p.M;   // compile-time M turns the x+1 corner into an immediate offset
+  const int M = kM > 0 ? kM : p.M;   // compile-time M turns the x+1 corner into an immediate offset
   LevelStride<kL> lv;
   if (kStatic) lv.init(tab, M);
 
@@ -349,22 +340,10 @@ fwd_d32_kernel(const D32Params p) {
           const Vec* r1 = r0 + (long long)wm * 8;
           // load and accumulate under ONE predicate per corner: no zero-fill of the landing
           // registers, and an invalid corner is never read (zero padding = "do not load")
-#if MSDA_FWD_PREDFMA
           if (r.x & 1) fma4(acc, w1, C::load(r0));
           if (r.x & 2) fma4(acc, w2, C::load(r0 + M * 8));
           if (r.x & 4) fma4(acc, w3, C::load(r1));
           if (r.x & 8) fma4(acc, w4, C::load(r1 + M * 8));
-#else
-          float4 v1 = make_float4(0.f, 0.f, 0.f, 0.f), v2 = v1, v3 = v1, v4 = v1;
-          if (r.x & 1) v1 = C::load(r0);
-          if (r.x & 2) v2 = C::load(r0 + M * 8);
-          if (r.x & 4) v3 = C::load(r1);
-          if (r.x & 8) v4 = C::load(r1 + M * 8);
-          fma4(acc, w1, v1);
-          fma4(acc, w2, v2);
-          fma4(acc, w3, v3);
-          fma4(acc, w4, v4);
-#endif
         }
       }
       st_stream(reinterpret_cast<float4*>(p.out) + item * 8 + sub, acc);
@@ -413,15 +392,7 @@ __device__ __forceinline__ void bwd_sample(const int4 r, const typename Chunk<VT
   const int dx = M * 8;
   const bool ok1 = live && (r.x & 1), ok2 = live && (r.x & 2), ok3 = live && (r.x & 4), ok4 = live && (r.x & 8);
   const float4 t = scale4(a, g);  // top_grad * attn_weight (cuh:115)
-  // One predicate per corner guards its load, its dot product and its reduction: an invalid corner
-  // is never read, gets no atomic (cuh:119-151) and needs no zero-filled landing registers.
-#if MSDA_BWD_PRED
-  float d1 = 0.f, d2 = 0.f, d3 = 0.f, d4 = 0.f;
-  if (ok1) { d1 = dot4(g, C::load(vb + o0)); G::red_add(gvb + o0, scale4(w1, t)); }
-  if (ok2) { d2 = dot4(g, C::load(vb + o0 + dx)); G::red_add(gvb + o0 + dx, scale4(w2, t)); }
-  if (ok3) { d3 = dot4(g, C::load(vb + o1)); G::red_add(gvb + o1, scale4(w3, t)); }
-  if (ok4) { d4 = dot4(g, C::load(vb + o1 + dx)); G::red_add(gvb + o1 + dx, scale4(w4, t)); }
-#else
+  // An invalid corner is never read and gets no atomic (cuh:119-151).
   float4 v1 = make_float4(0.f, 0.f, 0.f, 0.f), v2 = v1, v3 = v1, v4 = v1;
   if (ok1) v1 = C::load(vb + o0);
   if (ok2) v2 = C::load(vb + o0 + dx);
@@ -432,7 +403,6 @@ __device__ __forceinline__ void bwd_sample(const int4 r, const typename Chunk<VT
   if (ok3) G::red_add(gvb + o1, scale4(w3, t));
   if (ok4) G::red_add(gvb + o1 + dx, scale4(w4, t));
   const float d1 = dot4(g, v1), d2 = dot4(g, v2), d3 = dot4(g, v3), d4 = dot4(g, v4);
-#endif
   pa = w1 * d1 + w2 * d2 + w3 * d3 + w4 * d4;                    // cuh:156
   px = (hh * (d2 - d1) + lh * (d4 - d3)) * a * Wf;               // cuh:157
   py = (hw * (d3 - d1) + lw * (d4 - d2)) * a * Hf;               // cuh:158
@@ -460,7 +430,7 @@ bwd_d32_kernel(const D32Params p) {
   int4* warp_recs = reinterpret_cast<int4*>(smem_raw) + warp * (kItemsPerWarp * stride);
   const int4* my_recs = warp_recs + group * stride;
   int4* my_recs_w = warp_recs + group * stride;
-  const int M = (MSDA_STATIC_M && kM > 0) ? kM : p.M;   // compile-time M turns the x+1 corner into an immediate offset
+  const int M = kM > 0 ? kM : p.M;   // compile-time M turns the x+1 corner into an immediate offset
 
   const long long n_pass = (p.n_items + kItemsPerWarp - 1) / kItemsPerWarp;
   const long long pass_stride = (long long)gridDim.x * kD32Warps;
