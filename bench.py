@@ -244,8 +244,11 @@ def main():
     fwd_name, bwd_name = cabi.last_path(False), cabi.last_path(True)     # the kernels the timed steps ran
     clocks = sampler.stop() if sampler else None
     total_ms = t0.elapsed_time(t1)
-    fwd_ms = statistics.mean(e[0].elapsed_time(e[1]) for e in evs)
-    bwd_ms = statistics.mean(e[1].elapsed_time(e[2]) for e in evs)
+    fwd_all = [e[0].elapsed_time(e[1]) for e in evs]
+    bwd_all = [e[1].elapsed_time(e[2]) for e in evs]
+    fwd_ms, bwd_ms = statistics.mean(fwd_all), statistics.mean(bwd_all)
+    spread = {"fwd_ms_median": statistics.median(fwd_all), "fwd_ms_min": min(fwd_all),
+              "bwd_ms_median": statistics.median(bwd_all), "bwd_ms_min": min(bwd_all)}   # this rank's
     total_ms, fwd_ms, bwd_ms = sharding.max_over_ranks([total_ms, fwd_ms, bwd_ms], dist, "cuda")
     ms_per_step = total_ms / args.steps
     value = sharding.aggregate_throughput(wl.items, n_gpus, ms_per_step * 1e-3)
@@ -324,7 +327,7 @@ def main():
                     "fwd_gbs": bytes_fwd / (fwd_ms * 1e-3) / 1e9, "fwd_frac_of_peak": bytes_fwd / (fwd_ms * 1e-3) / 1e9 / peak,
                     "fwd_bwd_gbs": (bytes_fwd + bytes_bwd) / (ms_per_step * 1e-3) / 1e9,
                     "fwd_bwd_frac_of_peak": (bytes_fwd + bytes_bwd) / (ms_per_step * 1e-3) / 1e9 / peak,
-                    "fwd_bwd_frac_of_8TBs": (bytes_fwd + bytes_bwd) / (ms_per_step * 1e-3) / 1e9 / 8000.0},
+                    "fwd_bwd_frac_of_8TBs": (bytes_fwd + bytes_bwd) / (ms_per_step * 1e-3) / 1e9 / 8000.0, **spread},
         "roofline": {"bound": "hbm", "kernel": bwd_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes_per_launch": bytes_bwd,
                      "peak_source": peak_src},
@@ -334,6 +337,10 @@ def main():
         v, t, desc = cpu_port_baseline(args.workload, args.loc_dist, threads, 3, 1)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc,
                                 "ms_per_sample_step": t * 1e3}
+        # SURVEY 8d also asks for the single-thread figure (one timed run after one warm-up)
+        v1, t1_, _ = cpu_port_baseline(args.workload, args.loc_dist, 1, 1, 1)
+        line["cpu_baseline"]["single_thread_value"] = v1
+        line["cpu_baseline"]["single_thread_ms_per_sample_step"] = t1_ * 1e3
     else:
         line["cpu_baseline"] = None
     if extras:
