@@ -126,11 +126,19 @@ struct Chunk<float> {
   using Vec = float4;
   static __device__ __forceinline__ float4 load(const Vec* p) {
     MSDA_CHK(p, 16, 0);
+#ifdef MSDA_EXPERIMENT_NO_GATHER   // timing experiment: no value gathers (rows made up from the address)
+    const float f = __uint_as_float(0x3f800000u | ((unsigned)(size_t)p & 0xffffu));
+    return make_float4(f, f, f, f);
+#endif
     return __ldg(p);
   }
   // red.global.add.v4.f32: one 16 B reduction instead of four scalar atomics (sm_90+).
   static __device__ __forceinline__ void red_add(Vec* p, float4 v) {
     MSDA_CHK(p, 16, 1);
+#ifdef MSDA_EXPERIMENT_NO_RED   // timing experiment (tools/build_variants.sh): the backward without its reductions
+    if (v.x == 1.2345e-30f) *reinterpret_cast<volatile float*>(p) = v.y;
+    return;
+#endif
     asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
                  "f"(v.w)
                  : "memory");
