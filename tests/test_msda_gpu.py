@@ -821,6 +821,27 @@ def test_module_fused_prologue_equals_unfused(ref_dim):
         assert torch.allclose(p0[k], p1[k], rtol=1e-4, atol=1e-4 * float(p0[k].abs().max())), k
 
 
+def test_tensors_on_a_device_that_is_not_current():
+    """The reference takes no device guard: with tensors on cuda:1 while cuda:0 is current it
+    would launch on the wrong GPU.  The host layer here guards on value's device."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from uvhand_b200.functions import MSDeformAttnFunction
+    wl = Workload("dev1", 2, ((9, 13), (5, 7), (3, 4), (2, 2)), 40, loc_dist="twostage")
+    cpu = make_inputs(wl, seed=13, device="cpu")
+    with torch.cuda.device(0):
+        x = {k: v.to("cuda:1") for k, v in cpu.items()}
+        v = x["value"].requires_grad_(True)
+        out = MSDeformAttnFunction.apply(v, x["shapes"], x["lsi"], x["loc"], x["aw"], 64)
+        out.backward(x["grad_out"])
+        torch.cuda.synchronize(1)
+    assert out.device == torch.device("cuda:1") and v.grad.device == torch.device("cuda:1")
+    n = {k: t.numpy() for k, t in cpu.items()}
+    ref = oracle(n["value"], n["shapes"], n["lsi"], n["loc"], n["aw"], n["grad_out"])
+    close(out.detach().cpu().numpy(), ref["out"], FWD_RTOL)
+    close(v.grad.cpu().numpy(), ref["grad_value"], GRAD_RTOL)
+
+
 # ------------------------------------------------------------------------------------------------
 # launch hygiene (SURVEY.md 8f rank 3): the entry points never synchronise, so a stack of calls can be
 # captured in a CUDA graph and replayed
