@@ -24,7 +24,7 @@ def _env():
 
 def test_parity_suite_is_clean_under_the_bounds_checked_kernels():
     k = ("golden_f32 or golden_f64 or random_geometry_fuzz or shape_sweep or special_locations or invalid_corners "
-         "or touch_pattern or mid_size or fused_prologue_matches or fused_locations")
+         "or touch_pattern or mid_size or fused_prologue_matches or fused_prologue_fuzz or fused_locations")
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_msda_gpu.py"), "-m", "gpu",
                         "-x", "-q", "-k", k], env=_env(), capture_output=True, text=True, timeout=1500, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]

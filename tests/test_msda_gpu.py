@@ -306,7 +306,7 @@ def test_shape_sweep(shape, kind):
         check_all(res, ref, 1e-12, 1e-11)
 
 
-@pytest.mark.parametrize("seed", range(12))
+@pytest.mark.parametrize("seed", range(int(os.environ.get("MSDA_FUZZ_SEEDS", "12"))))
 def test_random_geometry_fuzz(seed):
     """Seeded random problems (ragged level sizes incl. 1xW / Hx1 / 1x1, any M, L, P with D = 32, locations
     from well outside to well inside, a sprinkle of NaN / inf / exact pixel centres / exact borders) through
@@ -756,6 +756,29 @@ def test_fused_prologue_matches_unfused_restatement(case):
     assert np.array_equal(res["grad_value"] != 0, unf["grad_value"] != 0)
     res2, _ = _run_fused(x, want_ref=False)
     assert np.array_equal(res2["grad_off"], res["grad_off"]) and res2["grad_ref"] is None
+
+
+@pytest.mark.parametrize("seed", range(int(os.environ.get("MSDA_FUZZ_SEEDS", "8"))))
+def test_fused_prologue_fuzz(seed):
+    """Random head / level / point counts and ragged level sizes through the fused kernels (both forward
+    decompositions), against the unfused restatement."""
+    rng = np.random.default_rng(7000 + seed)
+    L = int(rng.integers(1, 9))
+    P = int(rng.integers(1, 32 // L + 1))
+    M = int(rng.integers(1, 10))
+    N = int(rng.integers(1, 3))
+    Lq = int(rng.integers(1, 90))
+    levels = tuple((int(rng.integers(1, 14)), int(rng.integers(1, 14))) for _ in range(L))
+    x = _fused_inputs(N, M, L, P, Lq, levels, seed=90 + seed, ref_spread=1.5)
+    loc, a, ref = _fused_reference(x)
+    for split in (1, 2):
+        with Paths(0, 0, split):
+            res, _ = _run_fused(x)
+        close(res["out"], ref["out"], FWD_RTOL)
+        close(res["grad_value"], ref["grad_value"], GRAD_RTOL)
+        close(res["grad_off"], ref["grad_off"], GRAD_RTOL)
+        close(res["grad_logits"], ref["grad_logits"], GRAD_RTOL)
+        close(res["grad_ref"], ref["grad_ref"], GRAD_RTOL)
 
 
 def test_fused_locations_are_torch_bits():
