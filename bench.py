@@ -107,6 +107,16 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def cpu_model() -> str:
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.lower().startswith("model name"):
+                return ln.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def cpu_port_baseline(wl_name: str, loc_dist, threads: int, steps: int, warmup: int):
     """Times the grid_sample port (fwd + autograd bwd, fp32) on a bounded sample: ONE image of the
     workload (N=1, all queries).  Returns (items/s, description)."""
@@ -154,7 +164,7 @@ def run_reference(args):
                    "Lq": wl.Lq, "S": wl.S, "loc_dist": args.loc_dist or wl.loc_dist,
                    "note": "CPU port of ms_deform_attn_core_pytorch (F.grid_sample); each step = the sample below"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc,
-                         "torch": torch.__version__},
+                         "torch": torch.__version__, "cpu": cpu_model()},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -336,7 +346,7 @@ def main():
         threads = os.cpu_count() or 1
         v, t, desc = cpu_port_baseline(args.workload, args.loc_dist, threads, 3, 1)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc,
-                                "ms_per_sample_step": t * 1e3}
+                                "ms_per_sample_step": t * 1e3, "cpu": cpu_model()}
         # SURVEY 8d also asks for the single-thread figure (one timed run after one warm-up)
         v1, t1_, _ = cpu_port_baseline(args.workload, args.loc_dist, 1, 1, 1)
         line["cpu_baseline"]["single_thread_value"] = v1
