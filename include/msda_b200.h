@@ -168,8 +168,9 @@ int msda_host_fwd_bwd_f32(msda_host_plan *plan, const float *value, const int64_
  * "split_mode": which D=32 kernels serve a call: 0 = by problem size (small calls such as 300/900
  * decoder queries use the one-item-per-warp kernels, large ones four items per warp), 1 = never
  * split, 2 = always split; "bwd_maps": 2 = run the experimental fp32 backward that accumulates the
- * coarse levels of a small pyramid in shared memory (slower than the default on B200; kept for the
- * record).  None of these changes results beyond summation order.
+ * coarse levels of a small pyramid in shared memory; "bwd_window": 2 = run the experimental fp32
+ * backward that visits encoder queries as pixel tiles and gathers value rows from a staged shared-memory
+ * window (both slower than the default on B200; kept, tested, for the record).  None of these changes results beyond summation order.
  * Returns MSDA_OK or MSDA_ERR_BAD_OPTION. */
 int msda_b200_set_option(const char *key, int value);
 int msda_b200_get_option(const char *key, int *value);

@@ -42,26 +42,30 @@ def dev(a, dtype=None):
 class Paths:
     """Context manager forcing a kernel family.  fwd/bwd: 0 auto, 1 any-shape kernels;
     split: 0 auto (by problem size), 1 never (4 items per warp), 2 always (1 item per warp);
-    maps: 2 = the experimental backward with on-chip maps of the coarse levels (L = P = 4), else never."""
+    maps: 2 = the experimental backward with on-chip maps of the coarse levels (L = P = 4), else never;
+    window: 2 = the experimental backward gathering from a staged shared-memory window (L = P = 4), else never."""
 
-    def __init__(self, fwd=0, bwd=0, split=0, maps=1):
-        self.f, self.b, self.s, self.m = fwd, bwd, split, maps
+    def __init__(self, fwd=0, bwd=0, split=0, maps=1, window=1):
+        self.f, self.b, self.s, self.m, self.w = fwd, bwd, split, maps, window
 
     def __enter__(self):
         cabi.set_option("fwd_path", self.f)
         cabi.set_option("bwd_path", self.b)
         cabi.set_option("split_mode", self.s)
         cabi.set_option("bwd_maps", self.m)
+        cabi.set_option("bwd_window", self.w)
 
     def __exit__(self, *a):
         cabi.set_option("fwd_path", 0)
         cabi.set_option("bwd_path", 0)
         cabi.set_option("split_mode", 0)
         cabi.set_option("bwd_maps", 0)
+        cabi.set_option("bwd_window", 0)
 
 
 # the kernel families every parity case runs through (D = 32 shapes; "maps" applies to L = P = 4 only)
-FAMILIES = {"d32": (0, 0, 1, 1), "split": (0, 0, 2, 1), "maps": (0, 0, 1, 2), "anyshape": (1, 1, 0, 1)}
+FAMILIES = {"d32": (0, 0, 1, 1, 1), "split": (0, 0, 2, 1, 1), "maps": (0, 0, 1, 2, 1), "window": (0, 0, 1, 1, 2),
+            "anyshape": (1, 1, 0, 1, 1)}
 FAMILY_IDS = list(FAMILIES)
 
 
@@ -131,6 +135,7 @@ def test_golden_f32(path, forced):
         l4p4 = g["loc"].shape[3] == 4 and g["loc"].shape[4] == 4
         want = {"d32": ("fwd_d32_f32", "bwd_d32_f32"), "split": ("fwd_d32_split_f32", "bwd_d32_split_f32"),
                 "maps": ("fwd_d32_f32", "bwd_d32_maps_f32" if l4p4 else "bwd_d32_f32"),
+                "window": ("fwd_d32_f32", "bwd_d32_window_f32" if l4p4 else "bwd_d32_f32"),
                 "anyshape": ("fwd_generic_f32", "bwd_generic_f32")}[forced]
         assert (res["fwd_path"], res["bwd_path"]) == want
 
@@ -287,7 +292,7 @@ SHAPES = [
 
 
 @pytest.mark.parametrize("shape", SHAPES, ids=[f"N{s[0]}M{s[1]}D{s[2]}L{s[3]}P{s[4]}Lq{s[5]}" for s in SHAPES])
-@pytest.mark.parametrize("kind", ["f32", "f32-split", "f32-maps", "f64"])
+@pytest.mark.parametrize("kind", ["f32", "f32-split", "f32-maps", "f32-window", "f64"])
 def test_shape_sweep(shape, kind):
     N, M, D, L, P, Lq, levels = shape
     wl = Workload("s", N, levels, Lq, M=M, D=D, P=P, loc_dist="twostage")
@@ -295,8 +300,9 @@ def test_shape_sweep(shape, kind):
     x["loc"] = (x["loc"] * 0.4 + 0.5).astype(np.float32)   # mostly inside, some out
     split = 2 if kind == "f32-split" else 1                # 4-items-per-warp vs 1-item-per-warp kernels
     maps = 2 if kind == "f32-maps" else 1                  # backward with on-chip maps (only L = P = 4 takes it)
+    window = 2 if kind == "f32-window" else 1              # backward gathering from a staged window
     kind = kind.split("-")[0]
-    with Paths(0, 0, split, maps):
+    with Paths(0, 0, split, maps, window):
         res = run_cabi(kind, x["value"], x["shapes"], x["lsi"], x["loc"], x["aw"], x["grad_out"])
     variant = "f32x" if kind == "f32" else "f64"
     ref = oracle(x["value"], x["shapes"], x["lsi"], x["loc"], x["aw"], x["grad_out"], variant)

@@ -15,6 +15,7 @@
 
 #include "msda_d32.cuh"
 #include "msda_d32_maps.cuh"
+#include "msda_d32_window.cuh"
 #include "msda_generic.cuh"
 
 namespace {
@@ -25,6 +26,7 @@ std::atomic<int> g_fwd_path{0};
 std::atomic<int> g_bwd_path{0};
 std::atomic<int> g_bf16_direct{0};
 std::atomic<int> g_split_mode{0};   // 0 auto, 1 never, 2 always
+std::atomic<int> g_bwd_window{0};   // 2 = use the staged-window backward experiment (L = P = 4); otherwise never
 std::atomic<int> g_bwd_maps{0};     // 2 = use the on-chip-maps backward experiment (L = P = 4); otherwise never
 std::atomic<long long> g_launches{0};
 const char* g_last_path[2] = {"none", "none"};
@@ -207,6 +209,31 @@ int launch_bwd_maps(D32Params& p, cudaStream_t st) {
   return finish_launch(1);
 }
 
+// EXPERIMENT, never chosen automatically (option "bwd_window" = 2 selects it): fp32 backward for the encoder
+// layout whose value gathers come from a shared-memory window staged per (sample, head, 8x8 query tile)
+// -- msda_d32_window.cuh.  Correct in every test family, and slower than the plain kernel (C2 588 vs 498 us):
+// visiting queries tile by tile makes their reductions hit the same few coarse-level rows in bursts.
+bool use_window(const D32Params& p) {
+  return g_bwd_window.load() == 2 && p.L == kWinLevels && p.P == 4;
+}
+
+int launch_bwd_window(D32Params& p, cudaStream_t st) {
+  const size_t smem = window_smem_bytes();
+  auto go = [&](auto kernel) {
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    long long ctas = 2ll * sm_count();
+    const long long bound = ((long long)p.N * p.M * p.Lq + 63) / 64 + (long long)p.N * p.M * kWinLevels * 4;
+    if (ctas > bound) ctas = bound;
+    if (ctas < 1) ctas = 1;
+    register_extents(p.value, (size_t)p.N * p.S * p.M * 32 * sizeof(float), p.grad_value,
+                     (size_t)p.N * p.S * p.M * 32 * sizeof(float), st);
+    kernel<<<(int)ctas, kWinThreads, smem, st>>>(p);
+  };
+  if (p.M == 8) go(bwd_d32_window_kernel<8>);
+  else go(bwd_d32_window_kernel<0>);
+  return finish_launch(1);
+}
+
 template <typename T>
 int fwd_any(const T* value, const int64_t* shapes, const int64_t* lsi, const T* loc, const T* aw,
             int N, int S, int M, int D, int L, int Lq, int P, T* out, cudaStream_t st) {
@@ -284,6 +311,11 @@ int msda_b200_set_option(const char* key, int value) {
     g_bwd_maps.store(value);
     return MSDA_OK;
   }
+  if (!strcmp(key, "bwd_window")) {
+    if (value < 0 || value > 2) return MSDA_ERR_BAD_OPTION;
+    g_bwd_window.store(value);
+    return MSDA_OK;
+  }
   return MSDA_ERR_BAD_OPTION;
 }
 
@@ -294,6 +326,7 @@ int msda_b200_get_option(const char* key, int* value) {
   if (!strcmp(key, "bf16_direct_red")) { *value = g_bf16_direct.load(); return MSDA_OK; }
   if (!strcmp(key, "split_mode")) { *value = g_split_mode.load(); return MSDA_OK; }
   if (!strcmp(key, "bwd_maps")) { *value = g_bwd_maps.load(); return MSDA_OK; }
+  if (!strcmp(key, "bwd_window")) { *value = g_bwd_window.load(); return MSDA_OK; }
   return MSDA_ERR_BAD_OPTION;
 }
 
@@ -405,6 +438,10 @@ int msda_bwd_f32(const float* go, const float* value, const int64_t* shapes, con
     if (use_maps(p)) {
       g_last_path[1] = "bwd_d32_maps_f32";
       return launch_bwd_maps(p, st);
+    }
+    if (use_window(p)) {
+      g_last_path[1] = "bwd_d32_window_f32";
+      return launch_bwd_window(p, st);
     }
     bool sp = false;
     rc = launch_bwd_d32<float, float>(p, st, &sp);
