@@ -211,8 +211,8 @@ int launch_bwd_maps(D32Params& p, cudaStream_t st) {
 
 // EXPERIMENT, never chosen automatically (option "bwd_window" = 2 selects it): fp32 backward for the encoder
 // layout whose value gathers come from a shared-memory window staged per (sample, head, 8x8 query tile)
-// -- msda_d32_window.cuh.  Correct in every test family, and slower than the plain kernel (C2 588 vs 498 us):
-// visiting queries tile by tile makes their reductions hit the same few coarse-level rows in bursts.
+// -- msda_d32_window.cuh.  Correct in every test family, and slower than the plain kernel (C2 588 vs 498 us;
+// the header has the breakdown).
 bool use_window(const D32Params& p) {
   return g_bwd_window.load() == 2 && p.L == kWinLevels && p.P == 4;
 }

@@ -22,12 +22,11 @@
 // RESULT (B200): parity-green in every test family, and SLOWER than bwd_d32_kernel --
 //   DETR encoder 588 us vs 498 us (uniform locations, window useless: 606 vs 558), ARCTIC encoder 414 vs 309 us,
 // although the upper-bound experiment (gathers redirected to shared memory inside the plain kernel) reaches
-// 434 us.  What the upper bound did not have is the tile ORDER: 64 neighbouring queries of one head send
-// their 1024 coarse-level reductions to the same few dozen rows within microseconds, and same-address
-// reductions serialise in L2; the plain kernel's order (4 heads of one query per warp, CTAs striding over
-// the image) spreads them.  The same effect explains why every tile-ordered backward of this round lost
-// (profiles/r01_tuning_matrix.md).  Spatial coherence helps gathers and hurts scatter-adds; a tile-ordered
-// backward only makes sense together with on-chip combining of exactly those bursts.
+// 434 us.  The window itself pays (588 vs 606), what it rides on does not: the per-unit structure (two CTA
+// barriers, a serial window layout, 16-warp CTAs, ragged tile edges, 4 queries of one head per warp) costs
+// ~50 us even when the window is useless, and neighbouring tiles running at the same time send their
+// coarse-level reductions to the same rows (striding the tile order across the image recovers 22 us: 564).
+// Every tile-ordered backward of this round lost for these reasons (profiles/r01_tuning_matrix.md).
 // NOT selected automatically (option "bwd_window" = 2 runs it).
 #pragma once
 
@@ -108,7 +107,11 @@ bwd_d32_window_kernel(const D32Params p) {
   for (long long u = blockIdx.x; u < n_units; u += gridDim.x) {
     const int m = (int)(u % M);
     const long long rest = u / M;
+#ifdef MSDA_EXPERIMENT_WINDOW_STRIDE     // timing experiment: concurrently running CTAs far apart in the image
+    const int t = (int)(((rest % tab.n_tiles) * MSDA_EXPERIMENT_WINDOW_STRIDE) % tab.n_tiles);
+#else
     const int t = (int)(rest % tab.n_tiles);
+#endif
     const int b = (int)(rest / tab.n_tiles);
     int lq = 0, qy0 = 0, qx0 = 0, Hq = 1, Wq = 1;
     if (tab.spatial) {
