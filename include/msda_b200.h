@@ -167,10 +167,11 @@ int msda_host_fwd_bwd_f32(msda_host_plan *plan, const float *value, const int64_
  * torch host layer to pick msda_bwd_bf16's accumulation mode (0 = fp32 scratch, the default);
  * "split_mode": which D=32 kernels serve a call: 0 = by problem size (small calls such as 300/900
  * decoder queries use the one-item-per-warp kernels, large ones four items per warp), 1 = never
- * split, 2 = always split; "bwd_maps": 2 = run the experimental fp32 backward that accumulates the
- * coarse levels of a small pyramid in shared memory; "bwd_window": 2 = run the experimental fp32
- * backward that visits encoder queries as pixel tiles and gathers value rows from a staged shared-memory
- * window (both slower than the default on B200; kept, tested, for the record).  None of these changes results beyond summation order.
+ * split, 2 = always split; "bwd_tiles": the backward that combines grad_value rows on chip before they leave
+ * the SM (num_levels = num_point = 4): 0 = chosen by shape (encoder self-attention num_query == spatial_size, or a
+ * pyramid of at most 2048 tokens), 1 = never, 2 = whenever the shape is eligible.  None of these changes results
+ * beyond summation order.  Options are process-global (every thread and stream sees them); they exist for tests and
+ * benchmarks, production callers leave them at 0.
  * Returns MSDA_OK or MSDA_ERR_BAD_OPTION. */
 int msda_b200_set_option(const char *key, int value);
 int msda_b200_get_option(const char *key, int *value);

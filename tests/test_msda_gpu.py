@@ -42,30 +42,26 @@ def dev(a, dtype=None):
 class Paths:
     """Context manager forcing a kernel family.  fwd/bwd: 0 auto, 1 any-shape kernels;
     split: 0 auto (by problem size), 1 never (4 items per warp), 2 always (1 item per warp);
-    maps: 2 = the experimental backward with on-chip maps of the coarse levels (L = P = 4), else never;
-    window: 2 = the experimental backward gathering from a staged shared-memory window (L = P = 4), else never."""
+    tiles: the on-chip-combining backward (L = P = 4): 0 by shape, 1 never, 2 whenever the shape is eligible."""
 
-    def __init__(self, fwd=0, bwd=0, split=0, maps=1, window=1):
-        self.f, self.b, self.s, self.m, self.w = fwd, bwd, split, maps, window
+    def __init__(self, fwd=0, bwd=0, split=0, tiles=1):
+        self.f, self.b, self.s, self.t = fwd, bwd, split, tiles
 
     def __enter__(self):
         cabi.set_option("fwd_path", self.f)
         cabi.set_option("bwd_path", self.b)
         cabi.set_option("split_mode", self.s)
-        cabi.set_option("bwd_maps", self.m)
-        cabi.set_option("bwd_window", self.w)
+        cabi.set_option("bwd_tiles", self.t)
 
     def __exit__(self, *a):
         cabi.set_option("fwd_path", 0)
         cabi.set_option("bwd_path", 0)
         cabi.set_option("split_mode", 0)
-        cabi.set_option("bwd_maps", 0)
-        cabi.set_option("bwd_window", 0)
+        cabi.set_option("bwd_tiles", 0)
 
 
-# the kernel families every parity case runs through (D = 32 shapes; "maps" applies to L = P = 4 only)
-FAMILIES = {"d32": (0, 0, 1, 1, 1), "split": (0, 0, 2, 1, 1), "maps": (0, 0, 1, 2, 1), "window": (0, 0, 1, 1, 2),
-            "anyshape": (1, 1, 0, 1, 1)}
+# the kernel families every parity case runs through (D = 32 shapes; "tiles" applies to L = P = 4 only)
+FAMILIES = {"d32": (0, 0, 1, 1), "split": (0, 0, 2, 1), "tiles": (0, 0, 1, 2), "anyshape": (1, 1, 0, 1)}
 FAMILY_IDS = list(FAMILIES)
 
 
@@ -134,8 +130,7 @@ def test_golden_f32(path, forced):
     if g["value"].shape[3] == 32:
         l4p4 = g["loc"].shape[3] == 4 and g["loc"].shape[4] == 4
         want = {"d32": ("fwd_d32_f32", "bwd_d32_f32"), "split": ("fwd_d32_split_f32", "bwd_d32_split_f32"),
-                "maps": ("fwd_d32_f32", "bwd_d32_maps_f32" if l4p4 else "bwd_d32_f32"),
-                "window": ("fwd_d32_f32", "bwd_d32_window_f32" if l4p4 else "bwd_d32_f32"),
+                "tiles": ("fwd_d32_f32", "bwd_d32_tiles_f32" if l4p4 else "bwd_d32_f32"),
                 "anyshape": ("fwd_generic_f32", "bwd_generic_f32")}[forced]
         assert (res["fwd_path"], res["bwd_path"]) == want
 
@@ -292,17 +287,16 @@ SHAPES = [
 
 
 @pytest.mark.parametrize("shape", SHAPES, ids=[f"N{s[0]}M{s[1]}D{s[2]}L{s[3]}P{s[4]}Lq{s[5]}" for s in SHAPES])
-@pytest.mark.parametrize("kind", ["f32", "f32-split", "f32-maps", "f32-window", "f64"])
+@pytest.mark.parametrize("kind", ["f32", "f32-split", "f32-tiles", "f64"])
 def test_shape_sweep(shape, kind):
     N, M, D, L, P, Lq, levels = shape
     wl = Workload("s", N, levels, Lq, M=M, D=D, P=P, loc_dist="twostage")
     x = np_inputs(wl, 9, pad_frac=0.0, offset_px=1.0)
     x["loc"] = (x["loc"] * 0.4 + 0.5).astype(np.float32)   # mostly inside, some out
     split = 2 if kind == "f32-split" else 1                # 4-items-per-warp vs 1-item-per-warp kernels
-    maps = 2 if kind == "f32-maps" else 1                  # backward with on-chip maps (only L = P = 4 takes it)
-    window = 2 if kind == "f32-window" else 1              # backward gathering from a staged window
+    tiles = 2 if kind == "f32-tiles" else 1                # on-chip-combining backward (only L = P = 4 takes it)
     kind = kind.split("-")[0]
-    with Paths(0, 0, split, maps, window):
+    with Paths(0, 0, split, tiles):
         res = run_cabi(kind, x["value"], x["shapes"], x["lsi"], x["loc"], x["aw"], x["grad_out"])
     variant = "f32x" if kind == "f32" else "f64"
     ref = oracle(x["value"], x["shapes"], x["lsi"], x["loc"], x["aw"], x["grad_out"], variant)
@@ -421,8 +415,11 @@ def _full_size(wl, kind="f32", seed=0):
 def test_full_size_properties_f32(name):
     wl = WORKLOADS[name]
     t, out, gv, gl, ga = _full_size(wl)
-    # the 900/1098-query decoders are small enough for the one-item-per-warp kernels
-    want = ("fwd_d32_split_f32" if name.startswith("c4") else "fwd_d32_f32", "bwd_d32_f32")
+    # the 900/1098-query decoders are small enough for the one-item-per-warp forward; their queries have no
+    # relation to the (large) pyramid, so the backward reduces straight to L2.  Encoder self-attention and the
+    # small ARCTIC pyramid take the on-chip-combining backward.
+    want = ("fwd_d32_split_f32" if name.startswith("c4") else "fwd_d32_f32",
+            "bwd_d32_f32" if name.startswith("c4") else "bwd_d32_tiles_f32")
     assert (cabi.last_path(False), cabi.last_path(True)) == want
     g = t["grad_out"].view_as(out).double()
     # forward is linear in value and in the weights: <out, g> = <value, grad_value> = <w, grad_w>
@@ -506,7 +503,7 @@ def test_arctic_eval_batch_of_2048_frames_equals_the_reference_chunk_loop():
 def test_full_size_c5_bf16_properties():
     wl = WORKLOADS["c5_hires"]
     t, out, gv, gl, ga = _full_size(wl, kind="bf16")
-    assert cabi.last_path(False) == "fwd_d32_bf16" and cabi.last_path(True) == "bwd_d32_bf16_f32acc"
+    assert cabi.last_path(False) == "fwd_d32_bf16" and cabi.last_path(True) == "bwd_d32_tiles_bf16_f32acc"
     g = t["grad_out"].view_as(out).double()
     lhs = float((out.double() * g).sum())
     rhs_w = float((t["aw"].double() * ga.double()).sum())

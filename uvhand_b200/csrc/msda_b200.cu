@@ -14,8 +14,7 @@
 #include <new>
 
 #include "msda_d32.cuh"
-#include "msda_d32_maps.cuh"
-#include "msda_d32_window.cuh"
+#include "msda_d32_tiles.cuh"
 #include "msda_generic.cuh"
 
 namespace {
@@ -26,10 +25,10 @@ std::atomic<int> g_fwd_path{0};
 std::atomic<int> g_bwd_path{0};
 std::atomic<int> g_bf16_direct{0};
 std::atomic<int> g_split_mode{0};   // 0 auto, 1 never, 2 always
-std::atomic<int> g_bwd_window{0};   // 2 = use the staged-window backward experiment (L = P = 4); otherwise never
-std::atomic<int> g_bwd_maps{0};     // 2 = use the on-chip-maps backward experiment (L = P = 4); otherwise never
+std::atomic<int> g_bwd_tiles{0};    // on-chip-combining backward (L = P = 4): 0 by shape, 1 never, 2 whenever eligible
 std::atomic<long long> g_launches{0};
-const char* g_last_path[2] = {"none", "none"};
+// Introspection only (bench.py / tests read it right after their own call); last writer wins.
+std::atomic<const char*> g_last_path[2] = {{"none"}, {"none"}};
 
 // SM count of the CURRENT device (one process may drive several devices; cached per device).
 int sm_count() {
@@ -182,55 +181,48 @@ int launch_bwd_d32(D32Params& p, cudaStream_t st, bool* split = nullptr) {
   return finish_launch(1);
 }
 
-// EXPERIMENT, never chosen automatically (option "bwd_maps" = 2 selects it): fp32 backward with the coarse
-// levels of a small pyramid accumulated in warp-private shared-memory maps (msda_d32_maps.cuh).  Measured
-// at the ARCTIC shape it LOSES to the plain kernel (encoder 402 vs 306 us, decoder 125 vs 70 us) although
-// it halves the reductions sent to L2: profiles/r01_tuning_matrix.md.  Kept as the worked example behind
-// DESIGN.md 3.3's statement about on-chip combining, and tested like every other kernel family.
-bool use_maps(const D32Params& p) {
-  return g_bwd_maps.load() == 2 && p.L == 4 && p.P == 4;
+// On-chip-combining backward (msda_d32_tiles.cuh).  Eligible: L = P = 4.  Chosen by shape when the unit windows can
+// cover what the queries touch: encoder self-attention (Lq == S: query i is token i, tiles are 8x8 pixel blocks) or a
+// pyramid small enough to be windowed whole (S <= 2048 tokens: ARCTIC's 1045, any query order), and the call is
+// large enough to fill the device with units of 64 queries x 1 head.
+bool tiles_eligible(const D32Params& p) {
+  // 32-bit unit and row-chunk indices inside the kernel
+  const long long units_ub = (long long)p.N * p.M * ((long long)p.Lq / kTileQ + (long long)p.S / 8 + 16);
+  return p.L == kTileL && p.P == 4 && (long long)p.N * p.S * p.M * 8 < (1ll << 31) && units_ub < (1ll << 31) &&
+         (long long)p.N * p.Lq * p.M * kTileLP < (1ll << 31);
 }
 
-int launch_bwd_maps(D32Params& p, cudaStream_t st) {
-  const size_t smem = maps_smem_bytes(p.L * p.P);
-  auto go = [&](auto kernel) {
-    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    long long warps_needed = ((long long)p.N * p.M * p.Lq + 15) / 16;   // at least ~4 passes per warp
-    long long ctas = (warps_needed + kD32Warps - 1) / kD32Warps;
-    const long long cap = (long long)sm_count() * kMapsCtasPerSm;
-    if (ctas > cap) ctas = cap;
-    if (ctas < 1) ctas = 1;
-    register_extents(p.value, (size_t)p.N * p.S * p.M * 32 * sizeof(float), p.grad_value,
-                     (size_t)p.N * p.S * p.M * 32 * sizeof(float), st);
-    kernel<<<(int)ctas, kD32Threads, smem, st>>>(p);
-  };
-  if (p.M == 8) go(bwd_d32_maps_kernel<4, 4, 8>);
-  else go(bwd_d32_maps_kernel<4, 4, 0>);
-  return finish_launch(1);
+bool use_tiles(const D32Params& p) {
+  const int mode = g_bwd_tiles.load();
+  if (mode == 1 || !tiles_eligible(p)) return false;
+  if (mode == 2) return true;
+  const long long units = (long long)p.N * p.M * ((p.Lq + kTileQ - 1) / kTileQ);
+  return (p.Lq == p.S || p.S <= kWholeMaxRows) && units >= 2ll * sm_count();
 }
 
-// EXPERIMENT, never chosen automatically (option "bwd_window" = 2 selects it): fp32 backward for the encoder
-// layout whose value gathers come from a shared-memory window staged per (sample, head, 8x8 query tile)
-// -- msda_d32_window.cuh.  Correct in every test family, and slower than the plain kernel (C2 588 vs 498 us;
-// the header has the breakdown).
-bool use_window(const D32Params& p) {
-  return g_bwd_window.load() == 2 && p.L == kWinLevels && p.P == 4;
-}
-
-int launch_bwd_window(D32Params& p, cudaStream_t st) {
-  const size_t smem = window_smem_bytes();
-  auto go = [&](auto kernel) {
-    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    long long ctas = 2ll * sm_count();
-    const long long bound = ((long long)p.N * p.M * p.Lq + 63) / 64 + (long long)p.N * p.M * kWinLevels * 4;
-    if (ctas > bound) ctas = bound;
-    if (ctas < 1) ctas = 1;
-    register_extents(p.value, (size_t)p.N * p.S * p.M * 32 * sizeof(float), p.grad_value,
-                     (size_t)p.N * p.S * p.M * 32 * sizeof(float), st);
-    kernel<<<(int)ctas, kWinThreads, smem, st>>>(p);
-  };
-  if (p.M == 8) go(bwd_d32_window_kernel<8>);
-  else go(bwd_d32_window_kernel<0>);
+template <typename VT, typename GT>
+int launch_bwd_tiles(D32Params& p, cudaStream_t st) {
+  const int grid_mode = p.Lq == p.S ? 1 : 0;
+  auto kernel = bwd_d32_tile_kernel<VT, GT>;
+  const size_t smem = tile_smem_bytes();
+  static std::atomic<int> attr_done[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const int slot = dev >= 0 && dev < 64 ? dev : 0;
+  if (!attr_done[slot].load(std::memory_order_acquire)) {
+    const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    attr_done[slot].store(1, std::memory_order_release);
+  }
+  // units = N * tiles * M; the tile count of the pixel-block enumeration depends on the level shapes, which live on
+  // the device, so the grid is a fixed number of CTAs that stride over the units (two are resident per SM)
+  long long ctas = (long long)p.N * p.M * ((p.Lq + kTileQ - 1) / kTileQ + (grid_mode ? 4 * kTileL : 0));
+  const long long cap = (long long)sm_count() * 2 * MSDA_TILE_WAVES;
+  if (ctas > cap) ctas = cap;
+  if (ctas < 1) ctas = 1;
+  register_extents(p.value, (size_t)p.N * p.S * p.M * 32 * sizeof(VT), p.grad_value,
+                   (size_t)p.N * p.S * p.M * 32 * sizeof(GT), st);
+  kernel<<<(int)ctas, kTileThreads, smem, st>>>(p, grid_mode);
   return finish_launch(1);
 }
 
@@ -306,14 +298,9 @@ int msda_b200_set_option(const char* key, int value) {
     g_split_mode.store(value);
     return MSDA_OK;
   }
-  if (!strcmp(key, "bwd_maps")) {
+  if (!strcmp(key, "bwd_tiles")) {
     if (value < 0 || value > 2) return MSDA_ERR_BAD_OPTION;
-    g_bwd_maps.store(value);
-    return MSDA_OK;
-  }
-  if (!strcmp(key, "bwd_window")) {
-    if (value < 0 || value > 2) return MSDA_ERR_BAD_OPTION;
-    g_bwd_window.store(value);
+    g_bwd_tiles.store(value);
     return MSDA_OK;
   }
   return MSDA_ERR_BAD_OPTION;
@@ -325,14 +312,13 @@ int msda_b200_get_option(const char* key, int* value) {
   if (!strcmp(key, "bwd_path")) { *value = g_bwd_path.load(); return MSDA_OK; }
   if (!strcmp(key, "bf16_direct_red")) { *value = g_bf16_direct.load(); return MSDA_OK; }
   if (!strcmp(key, "split_mode")) { *value = g_split_mode.load(); return MSDA_OK; }
-  if (!strcmp(key, "bwd_maps")) { *value = g_bwd_maps.load(); return MSDA_OK; }
-  if (!strcmp(key, "bwd_window")) { *value = g_bwd_window.load(); return MSDA_OK; }
+  if (!strcmp(key, "bwd_tiles")) { *value = g_bwd_tiles.load(); return MSDA_OK; }
   return MSDA_ERR_BAD_OPTION;
 }
 
 int64_t msda_b200_launch_count(void) { return (int64_t)g_launches.load(); }
 
-const char* msda_b200_last_path(int backward) { return g_last_path[backward ? 1 : 0]; }
+const char* msda_b200_last_path(int backward) { return g_last_path[backward ? 1 : 0].load(); }
 
 // ---- forward ------------------------------------------------------------------------------
 
@@ -435,13 +421,9 @@ int msda_bwd_f32(const float* go, const float* value, const int64_t* shapes, con
     p.value = value; p.shapes = shapes; p.lsi = lsi; p.loc = loc; p.aw = aw; p.grad_out = go;
     p.grad_value = gv; p.grad_loc = gl; p.grad_aw = ga;
     p.N = N; p.S = S; p.M = M; p.L = L; p.Lq = Lq; p.P = P;
-    if (use_maps(p)) {
-      g_last_path[1] = "bwd_d32_maps_f32";
-      return launch_bwd_maps(p, st);
-    }
-    if (use_window(p)) {
-      g_last_path[1] = "bwd_d32_window_f32";
-      return launch_bwd_window(p, st);
+    if (use_tiles(p)) {
+      g_last_path[1] = "bwd_d32_tiles_f32";
+      return launch_bwd_tiles<float, float>(p, st);
     }
     bool sp = false;
     rc = launch_bwd_d32<float, float>(p, st, &sp);
@@ -487,8 +469,13 @@ int msda_bwd_bf16(const float* go, const uint16_t* value, const int64_t* shapes,
   if (gv_scratch) {
     // accurate mode: fp32 reductions into the scratch, one rounding to bf16 at the end
     p.grad_value = gv_scratch;
-    g_last_path[1] = "bwd_d32_bf16_f32acc";
-    rc = launch_bwd_d32<__nv_bfloat16, float>(p, st);
+    if (use_tiles(p)) {
+      g_last_path[1] = "bwd_d32_tiles_bf16_f32acc";
+      rc = launch_bwd_tiles<__nv_bfloat16, float>(p, st);
+    } else {
+      g_last_path[1] = "bwd_d32_bf16_f32acc";
+      rc = launch_bwd_d32<__nv_bfloat16, float>(p, st);
+    }
     if (rc) return rc;
     const long long n4 = (long long)N * S * M * 8;
     long long blocks = (n4 + 255) / 256;
@@ -499,6 +486,10 @@ int msda_bwd_bf16(const float* go, const uint16_t* value, const int64_t* shapes,
     return finish_launch(1);
   }
   p.grad_value = gv;
+  if (use_tiles(p)) {
+    g_last_path[1] = "bwd_d32_tiles_bf16";
+    return launch_bwd_tiles<__nv_bfloat16, __nv_bfloat16>(p, st);
+  }
   g_last_path[1] = "bwd_d32_bf16";
   return launch_bwd_d32<__nv_bfloat16, __nv_bfloat16>(p, st);
 }

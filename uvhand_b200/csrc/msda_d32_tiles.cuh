@@ -1,0 +1,525 @@
+// Backward for D = 32, L = P = 4 with grad_value combined ON CHIP before it leaves the SM
+// ("tile" backward).  Replaces, like bwd_d32_kernel, the reference's col2im kernels
+// (/root/reference/models/ops/src/cuda/ms_deform_im2col_cuda.cuh:301-403, bilinear part :87-159).
+//
+// Why: bwd_d32_kernel sends one 128 B reduction per bilinear corner to L2 (22.8 M rows = 2.9 GB at the
+// DETR-encoder shape) and is bound by the SM->L2 port at ~23 B/clk/SM (433 us for the reductions alone,
+// profiles/r01_microbench.md) although every grad_value row is hit ~64 times.  Shared-memory
+// read-modify-write of 128 B rows costs as much as the reduction it replaces (profiles/r01_microbench_smem.md).
+// This kernel turns the scatter around instead:
+//
+//   a corner's contribution is   coef * grad_out[q, m, :]   (coef = bilinear weight * attention weight)
+//
+// so per destination row r:  grad_value[r] = sum over (q, coef) in list(r) of coef * G[q], i.e. a sparse
+// (rows x queries) matrix times the tile's grad_out rows.  One UNIT = (sample b, tile of 64 queries, head m):
+//   P1  one thread per bilinear sample: geometry (sample_geom, the same routine as every other kernel),
+//       then per valid corner ONE 4-byte shared-memory counter increment (native ATOMS.ADD) on the
+//       destination row's slot in a per-level window; the returned rank places the 8-byte entry
+//       {coef, sample*4+corner} in a counting sort by destination row.
+//   P2  row-centric: 4 lanes own one destination row (8 channels each), 8 rows per warp.  The value row
+//       is loaded ONCE, the grad_value row is accumulated in REGISTERS over the row's entries
+//       (one broadcast LDS.64 + one 128 B G-row read per contribution, no read-modify-write anywhere)
+//       and leaves the SM as ONE red.global.add.v4.f32 per row and unit.  The same pass takes the dot
+//       products <G[q], value[r]> the location / weight gradients need and parks them per (sample, corner).
+//   P3  one thread per sample: grad_attn_weight and grad_sampling_loc from its four dots (cuh:156-158).
+// Rows are visited longest list first (counting sort by list length, lists longer than 32 are cut), so
+// the 8 rows of a warp pass have equal trip counts.
+//
+// Windows: per level min(W,22) x min(H,22) rows positioned at the mean sample position of the unit
+// (data-driven: correctness never depends on where the queries are), or the whole pyramid when it has
+// <= 2048 rows (ARCTIC: 1045).  Corners outside the window become single-entry rows of their own
+// ("leftover" rows: same code path, no combining).  Query tiles: 8x8 pixel blocks of each level when
+// Lq == S (encoder self-attention: query i is token i), else 64 consecutive queries.
+//
+// At the DETR-encoder shape a unit has 4096 contributions on ~1000 distinct rows: the SM->L2 port
+// carries a quarter of the bytes, value rows are read once per unit instead of once per corner.
+#pragma once
+
+#include "msda_d32.cuh"
+
+namespace msda {
+
+#ifndef MSDA_TILE_WAVES
+#define MSDA_TILE_WAVES 4     // grid = 2 resident CTAs per SM x this many; CTAs stride over the units
+#endif
+
+constexpr int kTileQ = 64;                        // queries per unit
+constexpr int kTileThreads = 512;
+constexpr int kTileWarps = kTileThreads / kWarp;
+constexpr int kTileLP = 16;                       // L = P = 4
+constexpr int kTileL = 4;
+constexpr int kTileSamples = kTileQ * kTileLP;    // 1024: two per thread
+constexpr int kTileEntries = kTileSamples * 4;    // 4096 corner contributions at most
+constexpr int kWinDim = 20;                       // window edge per level when the pyramid is large
+constexpr int kRowCap = 2048;                     // window rows + leftover rows
+constexpr int kWholeMaxRows = 1600;               // pyramids up to this many tokens are windowed whole
+constexpr int kRowsPerThread = kRowCap / kTileThreads;   // 4: one int4 of counters per thread in the scan
+constexpr int kSplit = 32;                        // longer entry lists are cut into virtual rows
+constexpr int kBins = kSplit + 1;
+constexpr int kRowListCap = kRowCap + kTileEntries / kSplit;
+constexpr int kBatchRows = 8;                     // 4 lanes per destination row
+static_assert(kRowsPerThread == 4, "the scan reads one int4 of counters per thread");
+
+struct TileUnit {          // decoded once per unit by thread 0
+  int m, b, lq, y0, x0, pad[3];
+};
+
+struct TileShared {
+  float4 G[kTileQ * 16];                // grad_out rows of the unit's queries, every row stored twice in a row (16 KB)
+  uint2 entries[kTileEntries];          // {coef, sample * 4 + corner}: window rows' lists from the front, leftovers from the back
+  float dbuf[kTileEntries];             // <G[q], value row> per (sample, corner) (16 KB)
+  float4 rec[kTileSamples];             // {lh, lw, attention weight, corner mask} per sample (16 KB)
+  int off[kRowCap + 8];                 // P1: counts; then exclusive offsets, off[R] = total
+  int rowtok[kRowCap + 8];              // token * M of every touched window row ([0, R)) and leftover row ((R, ..))
+  unsigned rowlist[kRowListCap];        // first entry << 18 | count << 12 | row, longest first
+  int whist[kTileWarps][kBins + 1];     // per-warp histogram of list lengths -> per-warp scatter cursors
+  int wsum[kTileWarps];
+  LevelTab tab;
+  int ww[kTileL], wh[kTileL], wbase[kTileL + 1], fixed[kTileL];
+  int tile0[kTileL + 1], tiles_x[kTileL];
+  int anchor_sum[kTileL][3];            // sum (w_low + 1), sum (h_low + 1), count of accepted samples per level
+  TileUnit unit;
+  int n_left, n_win, n_vrows, n_tiles, all_fixed, next_batch;
+};
+
+__device__ __forceinline__ float4 zero4() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+
+// unit -> (head, sample, tile origin).  grid mode: tile = an 8x8 pixel block of one level (query i is token i);
+// linear mode: 64 consecutive queries.
+__device__ __forceinline__ void decode_unit(TileShared& sh, int grid_mode, unsigned u, unsigned n_tiles, int M) {
+  TileUnit d;
+  d.m = (int)(u % (unsigned)M);
+  const unsigned um = u / (unsigned)M;
+  const int tile = (int)(um % n_tiles);
+  d.b = (int)(um / n_tiles);
+  if (!grid_mode) {
+    d.lq = 0; d.y0 = 0; d.x0 = tile * kTileQ;
+  } else {
+    d.lq = (tile >= sh.tile0[1]) + (tile >= sh.tile0[2]) + (tile >= sh.tile0[3]);
+    const int tt = tile - sh.tile0[d.lq];
+    const int ty = tt / sh.tiles_x[d.lq];
+    d.y0 = ty * 8;
+    d.x0 = (tt - ty * sh.tiles_x[d.lq]) * 8;
+  }
+  d.pad[0] = d.pad[1] = d.pad[2] = 0;
+  sh.unit = d;
+}
+
+// One corner contribution served by a single thread (the overflow path of the unit's row table).
+template <typename VT, typename GT>
+__device__ __noinline__ float lone_contribution(const typename Chunk<VT>::Vec* vr, typename Chunk<GT>::Vec* gr,
+                                                const float4* g_row, float coef) {
+  float d = 0.f;
+  for (int ch = 0; ch < 8; ++ch) {
+    const float4 g = g_row[ch];
+    d += dot4(g, Chunk<VT>::load(vr + ch));
+    Chunk<GT>::red_add(gr + ch, scale4(coef, g));
+  }
+  return d;
+}
+
+// A valid corner outside the unit's window: becomes a single-entry row of its own, its entry goes to the back of
+// the entry array right away.  Returns false when the row table is full (the caller then serves the corner alone).
+__device__ __noinline__ bool leftover_corner(TileShared& sh, int R, int row_m, float coef, unsigned sc) {
+  const int k = atomicAdd(&sh.n_left, 1);
+  if (k >= kRowCap - R - 1) return false;
+  sh.rowtok[R + 1 + k] = row_m;
+  sh.entries[kTileEntries - 1 - k] = make_uint2(__float_as_uint(coef), sc);
+  return true;
+}
+
+template <typename VT, typename GT>
+__global__ void __launch_bounds__(kTileThreads, 2)
+bwd_d32_tile_kernel(const D32Params p, const int grid_mode) {
+  using C = Chunk<VT>;
+  using Gc = Chunk<GT>;
+  using Vec = typename C::Vec;
+  using GVec = typename Gc::Vec;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  TileShared& sh = *reinterpret_cast<TileShared*>(smem_raw);
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int M = p.M;
+
+  // ---- once per CTA: level tables, window shapes, tile enumeration, cleared counters ------------------
+  if (t < kTileL) {
+    sh.tab.H[t] = (int)p.shapes[2 * t];
+    sh.tab.W[t] = (int)p.shapes[2 * t + 1];
+    sh.tab.start[t] = (int)p.lsi[t];
+  }
+  for (int i = t; i < kRowCap + 8; i += kTileThreads) sh.off[i] = 0;
+  for (int i = t; i < kTileWarps * (kBins + 1); i += kTileThreads) (&sh.whist[0][0])[i] = 0;
+  if (t < kTileL * 3) (&sh.anchor_sum[0][0])[t] = 0;
+  __syncthreads();
+  if (t == 0) {
+    const bool whole = p.S <= kWholeMaxRows;
+    int base = 0, tiles = 0, all_fixed = 1;
+    for (int l = 0; l < kTileL; ++l) {
+      const int H = sh.tab.H[l], W = sh.tab.W[l];
+      const int ww = whole ? W : min(W, kWinDim), wh = whole ? H : min(H, kWinDim);
+      sh.ww[l] = ww; sh.wh[l] = wh; sh.wbase[l] = base;
+      sh.fixed[l] = (ww == W && wh == H);
+      all_fixed &= sh.fixed[l];
+      base += ww * wh;
+      sh.tile0[l] = tiles;
+      sh.tiles_x[l] = (W + 7) >> 3;
+      tiles += ((W + 7) >> 3) * ((H + 7) >> 3);
+    }
+    sh.wbase[kTileL] = base;
+    sh.tile0[kTileL] = tiles;
+    sh.n_tiles = grid_mode ? tiles : (p.Lq + kTileQ - 1) / kTileQ;
+    sh.all_fixed = all_fixed;
+    sh.n_left = 0;
+    sh.next_batch = 0;
+    const unsigned nu = (unsigned)p.N * (unsigned)sh.n_tiles * (unsigned)M;
+    if (blockIdx.x < nu) decode_unit(sh, grid_mode, blockIdx.x, (unsigned)sh.n_tiles, M);
+  }
+  __syncthreads();
+  const unsigned n_tiles = (unsigned)sh.n_tiles;
+  const unsigned n_units = (unsigned)p.N * n_tiles * (unsigned)M;   // the host checked that this fits
+  const int R = sh.wbase[kTileL];             // window rows; leftover rows live at R + 1 + k
+  const bool all_fixed = sh.all_fixed;
+
+  // this thread's two samples: local query (t >> 4) + 32 i, level/point lp = t & 15
+  const int lp = t & 15, l = lp >> 2;
+  const int ql_dy = t >> 7, ql_dx = (t >> 4) & 7;          // grid mode: pixel of local query t >> 4 within the block
+
+  for (unsigned u = blockIdx.x; u < n_units; u += gridDim.x) {
+    const TileUnit un = sh.unit;
+    const int m = un.m, b = un.b;
+    const unsigned qbase = (unsigned)b * (unsigned)p.Lq;
+    const int Hl = sh.tab.H[l], Wl = sh.tab.W[l];
+    const int wwl = sh.ww[l], whl = sh.wh[l];
+    const bool fixedl = sh.fixed[l];
+    const int Hq = sh.tab.H[un.lq], Wq = sh.tab.W[un.lq], startq = sh.tab.start[un.lq];
+
+    // query index of local slot ql (0..63) of the tile, or -1
+    auto tile_query = [&](int ql, int dy, int dx) -> int {
+      if (!grid_mode) {
+        const int q = un.x0 + ql;
+        return q < p.Lq ? q : -1;
+      }
+      const int y = un.y0 + dy, x = un.x0 + dx;
+      return (y < Hq && x < Wq) ? startq + y * Wq + x : -1;
+    };
+
+    // ---- grad_out rows of the tile (row ql at G[16 ql .. 16 ql + 7] and again at + 8) -------------------
+    {
+      const int ql = t >> 3;
+      const int qq = tile_query(ql, ql >> 3, ql & 7);
+      float4 g = zero4();
+      if (qq >= 0) g = ld_stream(reinterpret_cast<const float4*>(p.grad_out) + (((qbase + qq) * M + m) * 8u + (t & 7)));
+      sh.G[ql * 16 + (t & 7)] = g;
+      sh.G[ql * 16 + 8 + (t & 7)] = g;
+    }
+
+    // ---- P1a: geometry of this thread's two samples ------------------------------------------------
+    float lh[2], lw[2], aw[2];
+    int h_low[2], w_low[2];
+    unsigned msk[2];
+    int packed = 0, accepted = 0;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int q = tile_query((t >> 4) + 32 * i, ql_dy + 4 * i, ql_dx);
+      msk[i] = 0; lh[i] = 0.f; lw[i] = 0.f; aw[i] = 0.f; h_low[i] = 0; w_low[i] = 0;
+      if (q >= 0) {
+        const unsigned gs = ((qbase + q) * M + m) * kTileLP + lp;
+        const float2 xy = ld_stream(reinterpret_cast<const float2*>(p.loc) + gs);
+        const float a = ld_stream(p.aw + gs);
+        SampleGeom<float> g;
+        if (sample_geom<float>(xy.x, xy.y, Hl, Wl, g)) {
+          msk[i] = g.mask | 16u;      // bit 4: accepted by the coarse test (a sample may have no valid corner)
+          lh[i] = g.lh; lw[i] = g.lw; aw[i] = a;
+          h_low[i] = g.h_low; w_low[i] = g.w_low;
+          packed += (g.w_low + 1) | ((g.h_low + 1) << 16);
+          accepted += 1;
+        }
+      }
+      sh.rec[t + kTileThreads * i] = make_float4(lh[i], lw[i], aw[i], __uint_as_float(msk[i]));
+    }
+    if (!all_fixed) {
+      // window anchor of non-whole levels: mean corner position of the unit's accepted samples
+      // (lanes with the same level: lane bits 0, 1 and 4 vary; 16 samples of <= 4094 fit the packed 16-bit sums)
+      packed += __shfl_xor_sync(kFull, packed, 1);
+      accepted += __shfl_xor_sync(kFull, accepted, 1);
+      packed += __shfl_xor_sync(kFull, packed, 2);
+      accepted += __shfl_xor_sync(kFull, accepted, 2);
+      packed += __shfl_xor_sync(kFull, packed, 16);
+      accepted += __shfl_xor_sync(kFull, accepted, 16);
+      if (!fixedl && (lane & 19) == 0 && accepted > 0) {
+        atomicAdd(&sh.anchor_sum[l][0], packed & 0xffff);
+        atomicAdd(&sh.anchor_sum[l][1], packed >> 16);
+        atomicAdd(&sh.anchor_sum[l][2], accepted);
+      }
+      __syncthreads();                                                                 // B1
+    }
+
+    // ---- P1b: count contributions per destination row ------------------------------------------------
+    int x0 = 0, y0 = 0;
+    if (!fixedl) {
+      const int n = sh.anchor_sum[l][2];
+      if (n > 0) {
+        const float inv = 1.f / (float)n;
+        x0 = (int)floorf((float)sh.anchor_sum[l][0] * inv - 0.5f * (float)wwl);
+        y0 = (int)floorf((float)sh.anchor_sum[l][1] * inv - 0.5f * (float)whl);
+        x0 = max(0, min(x0, Wl - wwl));
+        y0 = max(0, min(y0, Hl - whl));
+      }
+    }
+    // slot per corner: window row (12 bits) | rank << 12, or 0 when the corner has no entry in a window row's list
+    unsigned slot[2][4];
+    {
+      const int wbasel = sh.wbase[l], startl = sh.tab.start[l];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int ux = w_low[i] - x0, uy = h_low[i] - y0;
+        const bool inx[2] = {(unsigned)ux < (unsigned)wwl, (unsigned)(ux + 1) < (unsigned)wwl};
+        const bool iny[2] = {(unsigned)uy < (unsigned)whl, (unsigned)(uy + 1) < (unsigned)whl};
+        const int wr0 = wbasel + uy * wwl + ux;
+        const int tok0 = startl + h_low[i] * Wl + w_low[i];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          slot[i][c] = 0;
+          if ((msk[i] >> c) & 1u) {
+            const int tok = tok0 + (c & 1) + (c & 2 ? Wl : 0);
+            if (inx[c & 1] && iny[c >> 1]) {
+              const int wr = wr0 + (c & 1) + (c & 2 ? wwl : 0);
+              const int rank = atomicAdd(&sh.off[wr], 1);
+              if (rank == 0) sh.rowtok[wr] = tok * M;
+              slot[i][c] = 0x80000000u | ((unsigned)rank << 12) | (unsigned)wr;
+            } else {
+              const float wgt = (c & 2 ? lh[i] : 1.f - lh[i]) * (c & 1 ? lw[i] : 1.f - lw[i]);
+              const unsigned sc = (unsigned)((t + kTileThreads * i) * 4 + c);
+              if (!leftover_corner(sh, R, tok * M, wgt * aw[i], sc)) {
+                // no room left in the unit's row table: this thread alone serves the row (slow; only when
+                // the windows miss almost everything, which the host-side kernel choice avoids)
+                const long long ro = ((long long)b * p.S * M + (long long)tok * M + m) * 8;
+                sh.dbuf[sc] = lone_contribution<VT, GT>(reinterpret_cast<const Vec*>(p.value) + ro,
+                                                        reinterpret_cast<GVec*>(p.grad_value) + ro,
+                                                        sh.G + (sc >> 6) * 16, wgt * aw[i]);
+              }
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();                                                                   // B2
+
+    // ---- scan of the window rows' counts (thread: rows 4t..4t+3), histogram of list lengths ------------
+    int4 cnt4;
+    int excl;
+    {
+      cnt4 = reinterpret_cast<const int4*>(sh.off)[t];
+      const int r0 = t * kRowsPerThread;
+      if (r0 + 0 >= R) cnt4.x = 0;
+      if (r0 + 1 >= R) cnt4.y = 0;
+      if (r0 + 2 >= R) cnt4.z = 0;
+      if (r0 + 3 >= R) cnt4.w = 0;
+      const int cs[4] = {cnt4.x, cnt4.y, cnt4.z, cnt4.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = cs[j];
+        if (c > 0) {
+          if (c >> 5) atomicAdd(&sh.whist[warp][kSplit], c >> 5);
+          if (c & 31) atomicAdd(&sh.whist[warp][c & 31], 1);
+        }
+      }
+      const int run = cnt4.x + cnt4.y + cnt4.z + cnt4.w;
+      int inc = run;
+#pragma unroll
+      for (int o = 1; o < kWarp; o <<= 1) {
+        const int v = __shfl_up_sync(kFull, inc, o);
+        if (lane >= o) inc += v;
+      }
+      excl = inc - run;
+      if (lane == kWarp - 1) sh.wsum[warp] = inc;
+    }
+    __syncthreads();                                                                   // B3
+    int row_off0;      // offset of this thread's first row
+    {
+      int before = lane < warp ? sh.wsum[lane] : 0;
+      int total = lane < kTileWarps ? sh.wsum[lane] : 0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        before += __shfl_xor_sync(kFull, before, o);
+        total += __shfl_xor_sync(kFull, total, o);
+      }
+      row_off0 = before + excl;
+      // (rows >= R of the last touched int4 get offsets too: never read)
+      reinterpret_cast<int4*>(sh.off)[t] = make_int4(row_off0, row_off0 + cnt4.x, row_off0 + cnt4.x + cnt4.y,
+                                                     row_off0 + cnt4.x + cnt4.y + cnt4.z);
+      if (t == 0) sh.n_win = total;
+      if (warp == kTileWarps - 1) {
+        // per-warp scatter cursors: bins in descending length, warps in order within a bin
+        const int bin = kSplit - lane;           // lanes 0..31 <-> bins 32..1
+        int tot = 0;
+#pragma unroll
+        for (int w = 0; w < kTileWarps; ++w) tot += sh.whist[w][bin];
+        int inc = tot;
+#pragma unroll
+        for (int o = 1; o < kWarp; o <<= 1) {
+          const int v = __shfl_up_sync(kFull, inc, o);
+          if (lane >= o) inc += v;
+        }
+        int cur = inc - tot;
+#pragma unroll
+        for (int w = 0; w < kTileWarps; ++w) {
+          const int h = sh.whist[w][bin];
+          sh.whist[w][bin] = cur;
+          cur += h;
+        }
+        if (lane == kWarp - 1) sh.n_vrows = inc;
+      }
+    }
+    __syncthreads();                                                                   // B4
+
+    // ---- entries into their rows' lists; row list, longest first ----------------------------------------
+    const int n_left = min(sh.n_left, kRowCap - R - 1);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const float hh = 1.f - lh[i], hw = 1.f - lw[i];
+      const float ah = hh * aw[i], al = lh[i] * aw[i];
+      const float cf[4] = {ah * hw, ah * lw[i], al * hw, al * lw[i]};
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (slot[i][c]) {
+          const int pos = sh.off[slot[i][c] & 0xfff] + (int)((slot[i][c] >> 12) & 0x7ffff);
+          sh.entries[pos] = make_uint2(__float_as_uint(cf[c]), (unsigned)((t + kTileThreads * i) * 4 + c));
+        }
+      }
+    }
+    {
+      const int cs[4] = {cnt4.x, cnt4.y, cnt4.z, cnt4.w};
+      int o = row_off0;
+#pragma unroll
+      for (int j = 0; j < kRowsPerThread; ++j) {
+        const int c = cs[j];
+        if (c > 0) {
+          const unsigned r = (unsigned)(t * kRowsPerThread + j);
+          int done = 0;
+          for (int f = 0; f < (c >> 5); ++f, done += kSplit) {
+            const int pos = atomicAdd(&sh.whist[warp][kSplit], 1);
+            sh.rowlist[pos] = ((unsigned)(o + done) << 18) | (kSplit << 12) | r;
+          }
+          if (c & 31) {
+            const int pos = atomicAdd(&sh.whist[warp][c & 31], 1);
+            sh.rowlist[pos] = ((unsigned)(o + done) << 18) | ((unsigned)(c & 31) << 12) | r;
+          }
+          o += c;
+        }
+      }
+    }
+    const int n_vrows = sh.n_vrows;
+    for (int k = t; k < n_left; k += kTileThreads)
+      sh.rowlist[n_vrows + k] = ((unsigned)(kTileEntries - 1 - k) << 18) | (1u << 12) | (unsigned)(R + 1 + k);
+    __syncthreads();                                                                   // B5
+
+    // ---- P2: row-centric accumulation -------------------------------------------------------------------
+    // 4 lanes own one destination row; lane h of group g owns chunks h and 4 + h (adjacent lanes cover adjacent 16 B
+    // pieces: full sectors towards L2) and odd groups visit them in the opposite order so that the 8 lanes of a
+    // quarter-warp read 8 different chunks = all 32 banks.  With every G row stored twice in a row that order is
+    // "chunk first, then first + 4" for everybody.
+    {
+      const int n_rows = n_vrows + n_left;
+      const int g = lane >> 2, h = lane & 3;
+      const int first = 4 * (g & 1) + h;
+      const unsigned head = ((unsigned)b * (unsigned)p.S * (unsigned)M + (unsigned)m) * 8u;   // < 2^31 (host-checked)
+      const Vec* vb = reinterpret_cast<const Vec*>(p.value);
+      GVec* gvb = reinterpret_cast<GVec*>(p.grad_value);
+      const float4* Gl = sh.G + first;
+      for (;;) {
+        int j0 = 0;
+        if (lane == 0) j0 = atomicAdd(&sh.next_batch, kBatchRows);
+        j0 = __shfl_sync(kFull, j0, 0);
+        if (j0 >= n_rows) break;
+        const int j = j0 + g;
+        const bool has = j < n_rows;
+        const unsigned rl = has ? sh.rowlist[j] : 0u;
+        const int c = (int)((rl >> 12) & 63u);
+        const uint2* ep = sh.entries + (rl >> 18);
+        // lists are sorted by length: group 0 has the longest, group 7 the shortest of the pass
+        const int cmax = __shfl_sync(kFull, c, 0), cmin = __shfl_sync(kFull, c, 28);
+        const unsigned ro = head + (unsigned)sh.rowtok[rl & 0xfffu] * 8u;
+        float4 vA = zero4(), vB = zero4(), accA = zero4(), accB = zero4();
+        if (has) {
+          vA = C::load(vb + (ro + first));
+          vB = C::load(vb + (ro + (first ^ 4)));
+        }
+        int i = 0;
+        // every group has at least cmin entries: two per trip, no predicates; the two dot products are reduced
+        // together (lanes h = 0, 1 end up with the first, h = 2, 3 with the second)
+        for (; i + 2 <= cmin; i += 2) {
+          const uint2 e0 = ep[i], e1 = ep[i + 1];
+          const float4* g0 = Gl + ((e0.y >> 6) << 4);
+          const float4* g1 = Gl + ((e1.y >> 6) << 4);
+          const float4 a0 = g0[0], b0 = g0[4], a1 = g1[0], b1 = g1[4];
+          fma4(accA, __uint_as_float(e0.x), a0);
+          fma4(accB, __uint_as_float(e0.x), b0);
+          fma4(accA, __uint_as_float(e1.x), a1);
+          fma4(accB, __uint_as_float(e1.x), b1);
+          const float d0 = dot4(a0, vA) + dot4(b0, vB);
+          const float d1 = dot4(a1, vA) + dot4(b1, vB);
+          float r = ((h & 2) ? d1 : d0) + __shfl_xor_sync(kFull, (h & 2) ? d0 : d1, 2);
+          r += __shfl_xor_sync(kFull, r, 1);
+          if ((h & 1) == 0) sh.dbuf[(h & 2) ? e1.y : e0.y] = r;
+        }
+        for (; i < cmax; ++i) {
+          const bool act = i < c;
+          uint2 e = make_uint2(0u, 0u);
+          if (act) e = ep[i];
+          const float4* gq = Gl + ((e.y >> 6) << 4);
+          const float4 a0 = gq[0], b0 = gq[4];
+          fma4(accA, __uint_as_float(e.x), a0);
+          fma4(accB, __uint_as_float(e.x), b0);
+          float dp = dot4(a0, vA) + dot4(b0, vB);
+          dp += __shfl_xor_sync(kFull, dp, 1);
+          dp += __shfl_xor_sync(kFull, dp, 2);
+          if (act && h == 0) sh.dbuf[e.y] = dp;
+        }
+        if (has) {
+          Gc::red_add(gvb + (ro + first), accA);
+          Gc::red_add(gvb + (ro + (first ^ 4)), accB);
+        }
+      }
+    }
+    __syncthreads();                                                                   // B6
+
+    // ---- P3: per-sample gradients (cuh:156-158); clear the counters, decode the next unit ------------------------
+    {
+      const float Wf = (float)Wl, Hf = (float)Hl;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int q = tile_query((t >> 4) + 32 * i, ql_dy + 4 * i, ql_dx);
+        if (q >= 0) {
+          const unsigned gs = ((qbase + q) * M + m) * kTileLP + lp;
+          const float4 rc = sh.rec[t + kTileThreads * i];
+          const unsigned mk = __float_as_uint(rc.w);
+          float pa = 0.f, px = 0.f, py = 0.f;
+          if (mk & 15u) {
+            const float4 d = reinterpret_cast<const float4*>(sh.dbuf)[t + kTileThreads * i];
+            const float d1 = (mk & 1u) ? d.x : 0.f, d2 = (mk & 2u) ? d.y : 0.f;
+            const float d3 = (mk & 4u) ? d.z : 0.f, d4 = (mk & 8u) ? d.w : 0.f;
+            const float hh = 1.f - rc.x, hw = 1.f - rc.y;
+            pa = hh * hw * d1 + hh * rc.y * d2 + rc.x * hw * d3 + rc.x * rc.y * d4;
+            px = (hh * (d2 - d1) + rc.x * (d4 - d3)) * rc.z * Wf;
+            py = (hw * (d3 - d1) + rc.y * (d4 - d2)) * rc.z * Hf;
+          }
+          st_stream(p.grad_aw + gs, pa);
+          st_stream(reinterpret_cast<float2*>(p.grad_loc) + gs, make_float2(px, py));
+        }
+      }
+      for (int i = t; i < R; i += kTileThreads) sh.off[i] = 0;
+      for (int i = t; i < kTileWarps * (kBins + 1); i += kTileThreads) (&sh.whist[0][0])[i] = 0;
+      if (t < kTileL * 3) (&sh.anchor_sum[0][0])[t] = 0;
+      if (t == 0) {
+        sh.n_left = 0;
+        sh.next_batch = 0;
+        if (u + gridDim.x < n_units) decode_unit(sh, grid_mode, u + gridDim.x, n_tiles, M);
+      }
+    }
+    __syncthreads();                                                                   // B7
+  }
+}
+
+inline size_t tile_smem_bytes() { return sizeof(TileShared); }
+
+}  // namespace msda
