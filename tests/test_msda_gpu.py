@@ -42,26 +42,29 @@ def dev(a, dtype=None):
 class Paths:
     """Context manager forcing a kernel family.  fwd/bwd: 0 auto, 1 any-shape kernels;
     split: 0 auto (by problem size), 1 never (4 items per warp), 2 always (1 item per warp);
-    tiles: the on-chip-combining backward (L = P = 4): 0 by shape, 1 never, 2 whenever the shape is eligible."""
+    tiles: the on-chip-combining backward (L = P = 4): 0 by shape, 1 never, 2 whenever the shape is eligible;
+    wide: the 8-channels-per-lane forward (L = P = 4): 0 / 2 whenever eligible and not split, 1 never."""
 
-    def __init__(self, fwd=0, bwd=0, split=0, tiles=1):
-        self.f, self.b, self.s, self.t = fwd, bwd, split, tiles
+    def __init__(self, fwd=0, bwd=0, split=0, tiles=1, wide=1):
+        self.f, self.b, self.s, self.t, self.w = fwd, bwd, split, tiles, wide
 
     def __enter__(self):
         cabi.set_option("fwd_path", self.f)
         cabi.set_option("bwd_path", self.b)
         cabi.set_option("split_mode", self.s)
         cabi.set_option("bwd_tiles", self.t)
+        cabi.set_option("fwd_wide", self.w)
 
     def __exit__(self, *a):
         cabi.set_option("fwd_path", 0)
         cabi.set_option("bwd_path", 0)
         cabi.set_option("split_mode", 0)
         cabi.set_option("bwd_tiles", 0)
+        cabi.set_option("fwd_wide", 0)
 
 
 # the kernel families every parity case runs through (D = 32 shapes; "tiles" applies to L = P = 4 only)
-FAMILIES = {"d32": (0, 0, 1, 1), "split": (0, 0, 2, 1), "tiles": (0, 0, 1, 2), "anyshape": (1, 1, 0, 1)}
+FAMILIES = {"d32": (0, 0, 1, 1, 1), "split": (0, 0, 2, 1, 1), "tiles": (0, 0, 1, 2, 2), "anyshape": (1, 1, 0, 1, 1)}
 FAMILY_IDS = list(FAMILIES)
 
 
@@ -130,7 +133,7 @@ def test_golden_f32(path, forced):
     if g["value"].shape[3] == 32:
         l4p4 = g["loc"].shape[3] == 4 and g["loc"].shape[4] == 4
         want = {"d32": ("fwd_d32_f32", "bwd_d32_f32"), "split": ("fwd_d32_split_f32", "bwd_d32_split_f32"),
-                "tiles": ("fwd_d32_f32", "bwd_d32_tiles_f32" if l4p4 else "bwd_d32_f32"),
+                "tiles": ("fwd_d32_wide_f32" if l4p4 else "fwd_d32_f32", "bwd_d32_tiles_f32" if l4p4 else "bwd_d32_f32"),
                 "anyshape": ("fwd_generic_f32", "bwd_generic_f32")}[forced]
         assert (res["fwd_path"], res["bwd_path"]) == want
 
@@ -235,7 +238,7 @@ def test_mid_size_f32(dist, Lq, forced):
     check_all(res, oracle(x["value"], x["shapes"], x["lsi"], x["loc"], x["aw"], x["grad_out"]))
 
 
-@pytest.mark.parametrize("split", [1, 2], ids=["d32", "split"])
+@pytest.mark.parametrize("split", [1, 2, 3], ids=["d32", "split", "wide+tiles"])
 @pytest.mark.parametrize("direct", [False, True], ids=["f32acc", "direct-bf16x2"])
 @pytest.mark.parametrize("dist,Lq", [("encoder", MID_S), ("twostage", 300)])
 def test_mid_size_bf16(dist, Lq, direct, split):
@@ -243,11 +246,12 @@ def test_mid_size_bf16(dist, Lq, direct, split):
     x = np_inputs(wl, 4)
     v_bf16 = torch.from_numpy(x["value"]).to(torch.bfloat16)
     v_round = v_bf16.float().numpy()                      # what the kernel actually reads
-    with Paths(0, 0, split):
+    with Paths(0, 0, min(split, 2), 1, 1) if split < 3 else Paths(0, 0, 1, 2, 2):
         res = run_cabi("bf16", v_round, x["shapes"], x["lsi"], x["loc"], x["aw"], x["grad_out"], bf16_direct=direct)
     ref = oracle(v_round, x["shapes"], x["lsi"], x["loc"], x["aw"], x["grad_out"])
-    assert res["fwd_path"] == ("fwd_d32_bf16" if split == 1 else "fwd_d32_split_bf16")
-    assert res["bwd_path"] == ("bwd_d32_bf16" if direct else "bwd_d32_bf16_f32acc")
+    assert res["fwd_path"] == {1: "fwd_d32_bf16", 2: "fwd_d32_split_bf16", 3: "fwd_d32_wide_bf16"}[split]
+    tl = "tiles_" if split == 3 else ""
+    assert res["bwd_path"] == (f"bwd_d32_{tl}bf16" if direct else f"bwd_d32_{tl}bf16_f32acc")
     close(res["out"], ref["out"], FWD_RTOL)               # same rounded inputs -> fp32-level agreement
     close(res["grad_loc"], ref["grad_loc"], GRAD_RTOL)
     close(res["grad_aw"], ref["grad_aw"], GRAD_RTOL)
@@ -296,7 +300,7 @@ def test_shape_sweep(shape, kind):
     split = 2 if kind == "f32-split" else 1                # 4-items-per-warp vs 1-item-per-warp kernels
     tiles = 2 if kind == "f32-tiles" else 1                # on-chip-combining backward (only L = P = 4 takes it)
     kind = kind.split("-")[0]
-    with Paths(0, 0, split, tiles):
+    with Paths(0, 0, split, tiles, tiles):
         res = run_cabi(kind, x["value"], x["shapes"], x["lsi"], x["loc"], x["aw"], x["grad_out"])
     variant = "f32x" if kind == "f32" else "f64"
     ref = oracle(x["value"], x["shapes"], x["lsi"], x["loc"], x["aw"], x["grad_out"], variant)
@@ -479,7 +483,7 @@ def test_arctic_eval_batch_of_2048_frames_equals_the_reference_chunk_loop():
     gv_c = torch.zeros_like(gv)
     step = 64
     assert cabi.lib().msda_b200_check_im2col_step(N, step) == 0
-    with Paths(0, 0, 1, 0):    # chunks of 64 are small enough to pick the split forward; keep the kernels identical
+    with Paths(0, 0, 1, 0, 0):    # chunks of 64 are small enough to pick the split forward; keep the kernels identical
         for b0 in range(0, N, step):
             sl = slice(b0, b0 + step)
             dims = (step, S, M, D, L, Lq, P)
@@ -503,7 +507,7 @@ def test_arctic_eval_batch_of_2048_frames_equals_the_reference_chunk_loop():
 def test_full_size_c5_bf16_properties():
     wl = WORKLOADS["c5_hires"]
     t, out, gv, gl, ga = _full_size(wl, kind="bf16")
-    assert cabi.last_path(False) == "fwd_d32_bf16" and cabi.last_path(True) == "bwd_d32_tiles_bf16_f32acc"
+    assert cabi.last_path(False) == "fwd_d32_wide_bf16" and cabi.last_path(True) == "bwd_d32_tiles_bf16_f32acc"
     g = t["grad_out"].view_as(out).double()
     lhs = float((out.double() * g).sum())
     rhs_w = float((t["aw"].double() * ga.double()).sum())

@@ -15,6 +15,7 @@
 
 #include "msda_d32.cuh"
 #include "msda_d32_tiles.cuh"
+#include "msda_d32_wide.cuh"
 #include "msda_generic.cuh"
 
 namespace {
@@ -25,6 +26,7 @@ std::atomic<int> g_fwd_path{0};
 std::atomic<int> g_bwd_path{0};
 std::atomic<int> g_bf16_direct{0};
 std::atomic<int> g_split_mode{0};   // 0 auto, 1 never, 2 always
+std::atomic<int> g_fwd_wide{0};     // 8-channels-per-lane forward (L = P = 4): 0 by shape, 1 never, 2 whenever eligible
 std::atomic<int> g_bwd_tiles{0};    // on-chip-combining backward (L = P = 4): 0 by shape, 1 never, 2 whenever eligible
 std::atomic<long long> g_launches{0};
 // Introspection only (bench.py / tests read it right after their own call); last writer wins.
@@ -137,7 +139,7 @@ int split_grid(long long n_items, int resident_per_sm) {
 constexpr size_t kSplitSmem = (size_t)kD32Warps * kMaxLPD32 * 16;
 
 template <typename VT, bool kFuse = false>
-int launch_fwd_d32(D32Params& p, cudaStream_t st, bool* split = nullptr) {
+int launch_fwd_d32(D32Params& p, cudaStream_t st, bool* split = nullptr, bool* wide = nullptr) {
   const int LP = p.L * p.P;
   p.n_items = (long long)p.N * p.Lq * p.M;
   const bool sp = use_split(p.n_items, MSDA_FWD_MINB, false);
@@ -145,6 +147,23 @@ int launch_fwd_d32(D32Params& p, cudaStream_t st, bool* split = nullptr) {
   register_extents(p.value, (size_t)p.N * p.S * p.M * 32 * sizeof(VT), nullptr, 0, st);
   if (sp) {
     fwd_d32_split_kernel<VT, kFuse><<<split_grid(p.n_items, 4), kD32Threads, kSplitSmem, st>>>(p);
+    return finish_launch(1);
+  }
+  // 4 lanes per item, 8 items per warp pass (msda_d32_wide.cuh).  Chosen for bf16 values (64 B rows: one 128-bit load
+  // moves eight rows; C2 forward 135 -> 111 us).  For fp32 rows it is slower than 8 lanes per item (184 vs 152 us: a
+  // load instruction that touches 8 cache lines costs the L1 twice the cycles of one that touches 4), so fp32 takes
+  // it on request only (option "fwd_wide" = 2: tests).
+  const int wide_mode = g_fwd_wide.load();
+  if (p.L == 4 && p.P == 4 && (wide_mode == 2 || (wide_mode == 0 && sizeof(VT) == 2))) {
+    const long long n_pass = (p.n_items + kWideItems - 1) / kWideItems;
+    long long ctas = (n_pass + kD32Warps - 1) / kD32Warps;
+    const long long cap = (long long)sm_count() * MSDA_FWD_WIDE_MINB * MSDA_FWD_WIDE_WAVES;
+    if (ctas > cap) ctas = cap;
+    if (ctas < 1) ctas = 1;
+    if (split) *split = false;
+    if (p.M == 8) fwd_d32_wide_kernel<VT, 8, kFuse><<<(int)ctas, kD32Threads, wide_smem_bytes(), st>>>(p);
+    else fwd_d32_wide_kernel<VT, 0, kFuse><<<(int)ctas, kD32Threads, wide_smem_bytes(), st>>>(p);
+    if (wide) *wide = true;
     return finish_launch(1);
   }
   const int grid = d32_grid(p.n_items, MSDA_FWD_MINB, sizeof(VT) == 4 ? MSDA_FWD_WAVES : MSDA_FWD_WAVES_BF16);
@@ -303,6 +322,11 @@ int msda_b200_set_option(const char* key, int value) {
     g_bwd_tiles.store(value);
     return MSDA_OK;
   }
+  if (!strcmp(key, "fwd_wide")) {
+    if (value < 0 || value > 2) return MSDA_ERR_BAD_OPTION;
+    g_fwd_wide.store(value);
+    return MSDA_OK;
+  }
   return MSDA_ERR_BAD_OPTION;
 }
 
@@ -313,6 +337,7 @@ int msda_b200_get_option(const char* key, int* value) {
   if (!strcmp(key, "bf16_direct_red")) { *value = g_bf16_direct.load(); return MSDA_OK; }
   if (!strcmp(key, "split_mode")) { *value = g_split_mode.load(); return MSDA_OK; }
   if (!strcmp(key, "bwd_tiles")) { *value = g_bwd_tiles.load(); return MSDA_OK; }
+  if (!strcmp(key, "fwd_wide")) { *value = g_fwd_wide.load(); return MSDA_OK; }
   return MSDA_ERR_BAD_OPTION;
 }
 
@@ -345,9 +370,9 @@ int msda_fwd_f32(const float* value, const int64_t* shapes, const int64_t* lsi, 
     D32Params p{};
     p.value = value; p.shapes = shapes; p.lsi = lsi; p.loc = loc; p.aw = aw; p.out = out;
     p.N = N; p.S = S; p.M = M; p.L = L; p.Lq = Lq; p.P = P;
-    bool sp = false;
-    rc = launch_fwd_d32<float>(p, st, &sp);
-    g_last_path[0] = sp ? "fwd_d32_split_f32" : "fwd_d32_f32";
+    bool sp = false, wide = false;
+    rc = launch_fwd_d32<float>(p, st, &sp, &wide);
+    g_last_path[0] = sp ? "fwd_d32_split_f32" : wide ? "fwd_d32_wide_f32" : "fwd_d32_f32";
     return rc;
   }
   g_last_path[0] = "fwd_generic_f32";
@@ -394,9 +419,9 @@ int msda_fwd_bf16(const uint16_t* value, const int64_t* shapes, const int64_t* l
   D32Params p{};
   p.value = value; p.shapes = shapes; p.lsi = lsi; p.loc = loc; p.aw = aw; p.out = out;
   p.N = N; p.S = S; p.M = M; p.L = L; p.Lq = Lq; p.P = P;
-  bool sp = false;
-  rc = launch_fwd_d32<__nv_bfloat16>(p, st, &sp);
-  g_last_path[0] = sp ? "fwd_d32_split_bf16" : "fwd_d32_bf16";
+  bool sp = false, wide = false;
+  rc = launch_fwd_d32<__nv_bfloat16>(p, st, &sp, &wide);
+  g_last_path[0] = sp ? "fwd_d32_split_bf16" : wide ? "fwd_d32_wide_bf16" : "fwd_d32_bf16";
   return rc;
 }
 
@@ -516,9 +541,9 @@ int msda_fused_fwd_f32(const float* value, const int64_t* shapes, const int64_t*
   D32Params p{};
   p.value = value; p.shapes = shapes; p.lsi = lsi; p.loc = offsets; p.aw = logits; p.ref = ref; p.out = out;
   p.N = N; p.S = S; p.M = M; p.L = L; p.Lq = Lq; p.P = P;
-  bool sp = false;
-  rc = launch_fwd_d32<float, true>(p, st, &sp);
-  g_last_path[0] = sp ? "fwd_d32_split_fused_f32" : "fwd_d32_fused_f32";
+  bool sp = false, wide = false;
+  rc = launch_fwd_d32<float, true>(p, st, &sp, &wide);
+  g_last_path[0] = sp ? "fwd_d32_split_fused_f32" : wide ? "fwd_d32_wide_fused_f32" : "fwd_d32_fused_f32";
   return rc;
 }
 

@@ -79,7 +79,7 @@ struct TileShared {
   int tile0[kTileL + 1], tiles_x[kTileL];
   int anchor_sum[kTileL][3];            // sum (w_low + 1), sum (h_low + 1), count of accepted samples per level
   TileUnit unit;
-  int n_left, n_win, n_vrows, n_tiles, all_fixed, next_batch;
+  int n_left, n_win, n_vrows, n_tiles, all_fixed;
 };
 
 __device__ __forceinline__ float4 zero4() { return make_float4(0.f, 0.f, 0.f, 0.f); }
@@ -169,7 +169,6 @@ bwd_d32_tile_kernel(const D32Params p, const int grid_mode) {
     sh.n_tiles = grid_mode ? tiles : (p.Lq + kTileQ - 1) / kTileQ;
     sh.all_fixed = all_fixed;
     sh.n_left = 0;
-    sh.next_batch = 0;
     const unsigned nu = (unsigned)p.N * (unsigned)sh.n_tiles * (unsigned)M;
     if (blockIdx.x < nu) decode_unit(sh, grid_mode, blockIdx.x, (unsigned)sh.n_tiles, M);
   }
@@ -426,24 +425,35 @@ bwd_d32_tile_kernel(const D32Params p, const int grid_mode) {
       const Vec* vb = reinterpret_cast<const Vec*>(p.value);
       GVec* gvb = reinterpret_cast<GVec*>(p.grad_value);
       const float4* Gl = sh.G + first;
-      for (;;) {
-        int j0 = 0;
-        if (lane == 0) j0 = atomicAdd(&sh.next_batch, kBatchRows);
-        j0 = __shfl_sync(kFull, j0, 0);
-        if (j0 >= n_rows) break;
-        const int j = j0 + g;
-        const bool has = j < n_rows;
-        const unsigned rl = has ? sh.rowlist[j] : 0u;
+      // Passes (8 rows each) go to the warps in serpentine order: lists are sorted by length, so straight round robin
+      // would hand warp 0 the longest pass of every round.  The next pass's row and value chunks are requested
+      // before the current pass's entry loop (their L2 latency hides behind it).
+      const int n_pass = (n_rows + kBatchRows - 1) / kBatchRows;
+      auto pass_of = [&](int round) { return round * kTileWarps + ((round & 1) ? kTileWarps - 1 - warp : warp); };
+      unsigned rl_n = 0u;
+      float4 vA_n = zero4(), vB_n = zero4();
+      auto request = [&](int pass) {
+        const int j = pass * kBatchRows + g;
+        rl_n = 0u; vA_n = zero4(); vB_n = zero4();
+        if (pass < n_pass && j < n_rows) {
+          rl_n = sh.rowlist[j] | 0x40000000u;        // bit 30 (above the 12-bit entry offset): the slot holds a row
+          const unsigned ro = head + (unsigned)sh.rowtok[rl_n & 0xfffu] * 8u;
+          vA_n = C::load(vb + (ro + first));
+          vB_n = C::load(vb + (ro + (first ^ 4)));
+        }
+      };
+      request(pass_of(0));
+      for (int round = 0; pass_of(round) < n_pass; ++round) {
+        const unsigned rl = rl_n;
+        const float4 vA = vA_n, vB = vB_n;
+        request(pass_of(round + 1));
+        const bool has = (rl >> 30) & 1u;
         const int c = (int)((rl >> 12) & 63u);
-        const uint2* ep = sh.entries + (rl >> 18);
+        const uint2* ep = sh.entries + ((rl >> 18) & 0xfffu);
         // lists are sorted by length: group 0 has the longest, group 7 the shortest of the pass
         const int cmax = __shfl_sync(kFull, c, 0), cmin = __shfl_sync(kFull, c, 28);
         const unsigned ro = head + (unsigned)sh.rowtok[rl & 0xfffu] * 8u;
-        float4 vA = zero4(), vB = zero4(), accA = zero4(), accB = zero4();
-        if (has) {
-          vA = C::load(vb + (ro + first));
-          vB = C::load(vb + (ro + (first ^ 4)));
-        }
+        float4 accA = zero4(), accB = zero4();
         int i = 0;
         // every group has at least cmin entries: two per trip, no predicates; the two dot products are reduced
         // together (lanes h = 0, 1 end up with the first, h = 2, 3 with the second)
@@ -471,8 +481,8 @@ bwd_d32_tile_kernel(const D32Params p, const int grid_mode) {
           fma4(accA, __uint_as_float(e.x), a0);
           fma4(accB, __uint_as_float(e.x), b0);
           float dp = dot4(a0, vA) + dot4(b0, vB);
-          dp += __shfl_xor_sync(kFull, dp, 1);
-          dp += __shfl_xor_sync(kFull, dp, 2);
+          dp += __shfl_xor_sync(kFull, dp, 2);      // same association as the paired trips: results do not depend
+          dp += __shfl_xor_sync(kFull, dp, 1);      // on where in its row's list an entry landed
           if (act && h == 0) sh.dbuf[e.y] = dp;
         }
         if (has) {
@@ -512,7 +522,6 @@ bwd_d32_tile_kernel(const D32Params p, const int grid_mode) {
       if (t < kTileL * 3) (&sh.anchor_sum[0][0])[t] = 0;
       if (t == 0) {
         sh.n_left = 0;
-        sh.next_batch = 0;
         if (u + gridDim.x < n_units) decode_unit(sh, grid_mode, u + gridDim.x, n_tiles, M);
       }
     }
