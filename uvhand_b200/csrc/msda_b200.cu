@@ -223,7 +223,11 @@ template <typename VT, typename GT>
 int launch_bwd_tiles(D32Params& p, cudaStream_t st) {
   const int grid_mode = p.Lq == p.S ? 1 : 0;
   auto kernel = bwd_d32_tile_kernel<VT, GT>;
+#if MSDA_TILE_EXPERIMENT == 4      // timing experiment: one unit per SM (how much do two resident units overlap?)
+  const size_t smem = tile_smem_bytes() + 100 * 1024;
+#else
   const size_t smem = tile_smem_bytes();
+#endif
   static std::atomic<int> attr_done[64];
   int dev = 0;
   cudaGetDevice(&dev);

@@ -39,6 +39,9 @@
 
 namespace msda {
 
+#ifndef MSDA_TILE_EXPERIMENT
+#define MSDA_TILE_EXPERIMENT 0
+#endif
 #ifndef MSDA_TILE_WAVES
 #define MSDA_TILE_WAVES 4     // grid = 2 resident CTAs per SM x this many; CTAs stride over the units
 #endif
@@ -51,24 +54,26 @@ constexpr int kTileL = 4;
 constexpr int kTileSamples = kTileQ * kTileLP;    // 1024: two per thread
 constexpr int kTileEntries = kTileSamples * 4;    // 4096 corner contributions at most
 constexpr int kWinDim = 20;                       // window edge per level when the pyramid is large
-constexpr int kRowCap = 2048;                     // window rows + leftover rows
+constexpr int kRowCap = 1920;                     // window rows + leftover rows
 constexpr int kWholeMaxRows = 1600;               // pyramids up to this many tokens are windowed whole
-constexpr int kRowsPerThread = kRowCap / kTileThreads;   // 4: one int4 of counters per thread in the scan
+constexpr int kRowsPerThread = 4;                 // one int4 of counters per thread in the scan (threads < kRowCap / 4)
 constexpr int kSplit = 32;                        // longer entry lists are cut into virtual rows
 constexpr int kBins = kSplit + 1;
 constexpr int kRowListCap = kRowCap + kTileEntries / kSplit;
 constexpr int kBatchRows = 8;                     // 4 lanes per destination row
-static_assert(kRowsPerThread == 4, "the scan reads one int4 of counters per thread");
+static_assert(kRowCap % 4 == 0 && kRowCap / 4 <= kTileThreads, "the scan reads one int4 of counters per thread");
 
 struct TileUnit {          // decoded once per unit by thread 0
   int m, b, lq, y0, x0, pad[3];
 };
 
 struct TileShared {
-  float4 G[kTileQ * 16];                // grad_out rows of the unit's queries, every row stored twice in a row (16 KB)
+  float4 G[kTileQ * 8];                 // grad_out rows of the unit's queries (8 KB)
   uint2 entries[kTileEntries];          // {coef, sample * 4 + corner}: window rows' lists from the front, leftovers from the back
   float dbuf[kTileEntries];             // <G[q], value row> per (sample, corner) (16 KB)
   float4 rec[kTileSamples];             // {lh, lw, attention weight, corner mask} per sample (16 KB)
+  float2 stage_loc[kTileSamples];       // the NEXT unit's sampling locations / weights, copied asynchronously while
+  float stage_aw[kTileSamples];         // this unit is processed (12 KB): their HBM latency never heads a unit
   int off[kRowCap + 8];                 // P1: counts; then exclusive offsets, off[R] = total
   int rowtok[kRowCap + 8];              // token * M of every touched window row ([0, R)) and leftover row ((R, ..))
   unsigned rowlist[kRowListCap];        // first entry << 18 | count << 12 | row, longest first
@@ -78,15 +83,16 @@ struct TileShared {
   int ww[kTileL], wh[kTileL], wbase[kTileL + 1], fixed[kTileL];
   int tile0[kTileL + 1], tiles_x[kTileL];
   int anchor_sum[kTileL][3];            // sum (w_low + 1), sum (h_low + 1), count of accepted samples per level
-  TileUnit unit;
-  int n_left, n_win, n_vrows, n_tiles, all_fixed;
+  TileUnit unit[2];                     // this unit and the next one (alternating)
+  int n_left, n_win, n_vrows, n_tiles, all_fixed, next_pass;
 };
 
 __device__ __forceinline__ float4 zero4() { return make_float4(0.f, 0.f, 0.f, 0.f); }
 
 // unit -> (head, sample, tile origin).  grid mode: tile = an 8x8 pixel block of one level (query i is token i);
 // linear mode: 64 consecutive queries.
-__device__ __forceinline__ void decode_unit(TileShared& sh, int grid_mode, unsigned u, unsigned n_tiles, int M) {
+__device__ __forceinline__ void decode_unit(TileShared& sh, int slot, int grid_mode, unsigned u, unsigned n_tiles,
+                                            int M) {
   TileUnit d;
   d.m = (int)(u % (unsigned)M);
   const unsigned um = u / (unsigned)M;
@@ -102,7 +108,51 @@ __device__ __forceinline__ void decode_unit(TileShared& sh, int grid_mode, unsig
     d.x0 = (tt - ty * sh.tiles_x[d.lq]) * 8;
   }
   d.pad[0] = d.pad[1] = d.pad[2] = 0;
-  sh.unit = d;
+  sh.unit[slot] = d;
+}
+
+__device__ __forceinline__ void cp_async_4(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_8(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// query index of local slot (ql; pixel dy, dx of the 8x8 block in grid mode) of a unit's tile, or -1
+__device__ __forceinline__ int unit_query(const TileShared& sh, const TileUnit& un, int grid_mode, int Lq, int ql, int dy,
+                                          int dx) {
+  if (!grid_mode) {
+    const int q = un.x0 + ql;
+    return q < Lq ? q : -1;
+  }
+  const int y = un.y0 + dy, x = un.x0 + dx, W = sh.tab.W[un.lq];
+  return (y < sh.tab.H[un.lq] && x < W) ? sh.tab.start[un.lq] + y * W + x : -1;
+}
+
+// Asynchronous copies of a unit's inputs: every thread copies exactly what it will read itself (its two samples),
+// plus one 16 B chunk of the tile's grad_out rows (read by others: a barrier follows the wait).
+__device__ __forceinline__ void request_samples(TileShared& sh, const D32Params& p, const TileUnit& un, int grid_mode, int t) {
+  const unsigned qbase = (unsigned)un.b * (unsigned)p.Lq;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int q = unit_query(sh, un, grid_mode, p.Lq, (t >> 4) + 32 * i, (t >> 7) + 4 * i, (t >> 4) & 7);
+    if (q >= 0) {
+      const unsigned gs = ((qbase + q) * p.M + un.m) * kTileLP + (t & 15);
+      cp_async_8(&sh.stage_loc[t + kTileThreads * i], reinterpret_cast<const float2*>(p.loc) + gs);
+      cp_async_4(&sh.stage_aw[t + kTileThreads * i], p.aw + gs);
+    }
+  }
+}
+__device__ __forceinline__ void request_grad_rows(TileShared& sh, const D32Params& p, const TileUnit& un, int grid_mode, int t) {
+  const int ql = t >> 3;
+  const int qq = unit_query(sh, un, grid_mode, p.Lq, ql, ql >> 3, ql & 7);
+  const unsigned qbase = (unsigned)un.b * (unsigned)p.Lq;
+  if (qq >= 0) cp_async_16(&sh.G[t], reinterpret_cast<const float4*>(p.grad_out) + (((qbase + qq) * p.M + un.m) * 8u + (t & 7)));
+  else sh.G[t] = zero4();
 }
 
 // One corner contribution served by a single thread (the overflow path of the unit's row table).
@@ -169,8 +219,9 @@ bwd_d32_tile_kernel(const D32Params p, const int grid_mode) {
     sh.n_tiles = grid_mode ? tiles : (p.Lq + kTileQ - 1) / kTileQ;
     sh.all_fixed = all_fixed;
     sh.n_left = 0;
+    sh.next_pass = 0;
     const unsigned nu = (unsigned)p.N * (unsigned)sh.n_tiles * (unsigned)M;
-    if (blockIdx.x < nu) decode_unit(sh, grid_mode, blockIdx.x, (unsigned)sh.n_tiles, M);
+    if (blockIdx.x < nu) decode_unit(sh, 0, grid_mode, blockIdx.x, (unsigned)sh.n_tiles, M);
   }
   __syncthreads();
   const unsigned n_tiles = (unsigned)sh.n_tiles;
@@ -182,8 +233,15 @@ bwd_d32_tile_kernel(const D32Params p, const int grid_mode) {
   const int lp = t & 15, l = lp >> 2;
   const int ql_dy = t >> 7, ql_dx = (t >> 4) & 7;          // grid mode: pixel of local query t >> 4 within the block
 
-  for (unsigned u = blockIdx.x; u < n_units; u += gridDim.x) {
-    const TileUnit un = sh.unit;
+  if (blockIdx.x < n_units) {
+    request_samples(sh, p, sh.unit[0], grid_mode, t);
+    request_grad_rows(sh, p, sh.unit[0], grid_mode, t);
+  }
+  int slot_u = 0;
+  for (unsigned u = blockIdx.x; u < n_units; u += gridDim.x, slot_u ^= 1) {
+    const TileUnit un = sh.unit[slot_u];
+    const bool more = u + gridDim.x < n_units;
+    if (t == 0 && more) decode_unit(sh, slot_u ^ 1, grid_mode, u + gridDim.x, n_tiles, M);
     const int m = un.m, b = un.b;
     const unsigned qbase = (unsigned)b * (unsigned)p.Lq;
     const int Hl = sh.tab.H[l], Wl = sh.tab.W[l];
@@ -201,17 +259,8 @@ bwd_d32_tile_kernel(const D32Params p, const int grid_mode) {
       return (y < Hq && x < Wq) ? startq + y * Wq + x : -1;
     };
 
-    // ---- grad_out rows of the tile (row ql at G[16 ql .. 16 ql + 7] and again at + 8) -------------------
-    {
-      const int ql = t >> 3;
-      const int qq = tile_query(ql, ql >> 3, ql & 7);
-      float4 g = zero4();
-      if (qq >= 0) g = ld_stream(reinterpret_cast<const float4*>(p.grad_out) + (((qbase + qq) * M + m) * 8u + (t & 7)));
-      sh.G[ql * 16 + (t & 7)] = g;
-      sh.G[ql * 16 + 8 + (t & 7)] = g;
-    }
-
     // ---- P1a: geometry of this thread's two samples ------------------------------------------------
+    cp_async_wait_all();         // this thread's own copies (its samples, its chunk of G) have landed
     float lh[2], lw[2], aw[2];
     int h_low[2], w_low[2];
     unsigned msk[2];
@@ -221,9 +270,8 @@ bwd_d32_tile_kernel(const D32Params p, const int grid_mode) {
       const int q = tile_query((t >> 4) + 32 * i, ql_dy + 4 * i, ql_dx);
       msk[i] = 0; lh[i] = 0.f; lw[i] = 0.f; aw[i] = 0.f; h_low[i] = 0; w_low[i] = 0;
       if (q >= 0) {
-        const unsigned gs = ((qbase + q) * M + m) * kTileLP + lp;
-        const float2 xy = ld_stream(reinterpret_cast<const float2*>(p.loc) + gs);
-        const float a = ld_stream(p.aw + gs);
+        const float2 xy = sh.stage_loc[t + kTileThreads * i];
+        const float a = sh.stage_aw[t + kTileThreads * i];
         SampleGeom<float> g;
         if (sample_geom<float>(xy.x, xy.y, Hl, Wl, g)) {
           msk[i] = g.mask | 16u;      // bit 4: accepted by the coarse test (a sample may have no valid corner)
@@ -233,7 +281,8 @@ bwd_d32_tile_kernel(const D32Params p, const int grid_mode) {
           accepted += 1;
         }
       }
-      sh.rec[t + kTileThreads * i] = make_float4(lh[i], lw[i], aw[i], __uint_as_float(msk[i]));
+      // (the query index rides along so that the epilogue needs nothing that lived through the row pass)
+      sh.rec[t + kTileThreads * i] = make_float4(lh[i], lw[i], aw[i], __uint_as_float(((unsigned)(q + 1) << 5) | msk[i]));
     }
     if (!all_fixed) {
       // window anchor of non-whole levels: mean corner position of the unit's accepted samples
@@ -249,8 +298,8 @@ bwd_d32_tile_kernel(const D32Params p, const int grid_mode) {
         atomicAdd(&sh.anchor_sum[l][1], packed >> 16);
         atomicAdd(&sh.anchor_sum[l][2], accepted);
       }
-      __syncthreads();                                                                 // B1
     }
+    __syncthreads();                                                                   // B1 (also: G, next unit's slot)
 
     // ---- P1b: count contributions per destination row ------------------------------------------------
     int x0 = 0, y0 = 0;
@@ -294,7 +343,7 @@ bwd_d32_tile_kernel(const D32Params p, const int grid_mode) {
                 const long long ro = ((long long)b * p.S * M + (long long)tok * M + m) * 8;
                 sh.dbuf[sc] = lone_contribution<VT, GT>(reinterpret_cast<const Vec*>(p.value) + ro,
                                                         reinterpret_cast<GVec*>(p.grad_value) + ro,
-                                                        sh.G + (sc >> 6) * 16, wgt * aw[i]);
+                                                        sh.G + (sc >> 6) * 8, wgt * aw[i]);
               }
             }
           }
@@ -302,12 +351,13 @@ bwd_d32_tile_kernel(const D32Params p, const int grid_mode) {
       }
     }
     __syncthreads();                                                                   // B2
+    if (more) request_samples(sh, p, sh.unit[slot_u ^ 1], grid_mode, t);
 
     // ---- scan of the window rows' counts (thread: rows 4t..4t+3), histogram of list lengths ------------
     int4 cnt4;
     int excl;
     {
-      cnt4 = reinterpret_cast<const int4*>(sh.off)[t];
+      cnt4 = t < kRowCap / 4 ? reinterpret_cast<const int4*>(sh.off)[t] : make_int4(0, 0, 0, 0);
       const int r0 = t * kRowsPerThread;
       if (r0 + 0 >= R) cnt4.x = 0;
       if (r0 + 1 >= R) cnt4.y = 0;
@@ -344,8 +394,9 @@ bwd_d32_tile_kernel(const D32Params p, const int grid_mode) {
       }
       row_off0 = before + excl;
       // (rows >= R of the last touched int4 get offsets too: never read)
-      reinterpret_cast<int4*>(sh.off)[t] = make_int4(row_off0, row_off0 + cnt4.x, row_off0 + cnt4.x + cnt4.y,
-                                                     row_off0 + cnt4.x + cnt4.y + cnt4.z);
+      if (t < kRowCap / 4)
+        reinterpret_cast<int4*>(sh.off)[t] = make_int4(row_off0, row_off0 + cnt4.x, row_off0 + cnt4.x + cnt4.y,
+                                                       row_off0 + cnt4.x + cnt4.y + cnt4.z);
       if (t == 0) sh.n_win = total;
       if (warp == kTileWarps - 1) {
         // per-warp scatter cursors: bins in descending length, warps in order within a bin
@@ -415,8 +466,7 @@ bwd_d32_tile_kernel(const D32Params p, const int grid_mode) {
     // ---- P2: row-centric accumulation -------------------------------------------------------------------
     // 4 lanes own one destination row; lane h of group g owns chunks h and 4 + h (adjacent lanes cover adjacent 16 B
     // pieces: full sectors towards L2) and odd groups visit them in the opposite order so that the 8 lanes of a
-    // quarter-warp read 8 different chunks = all 32 banks.  With every G row stored twice in a row that order is
-    // "chunk first, then first + 4" for everybody.
+    // quarter-warp read 8 different chunks = all 32 banks.
     {
       const int n_rows = n_vrows + n_left;
       const int g = lane >> 2, h = lane & 3;
@@ -424,12 +474,28 @@ bwd_d32_tile_kernel(const D32Params p, const int grid_mode) {
       const unsigned head = ((unsigned)b * (unsigned)p.S * (unsigned)M + (unsigned)m) * 8u;   // < 2^31 (host-checked)
       const Vec* vb = reinterpret_cast<const Vec*>(p.value);
       GVec* gvb = reinterpret_cast<GVec*>(p.grad_value);
-      const float4* Gl = sh.G + first;
-      // Passes (8 rows each) go to the warps in serpentine order: lists are sorted by length, so straight round robin
-      // would hand warp 0 the longest pass of every round.  The next pass's row and value chunks are requested
-      // before the current pass's entry loop (their L2 latency hides behind it).
+      const float4* GA = sh.G + first;
+      const float4* GB = sh.G + (first ^ 4);
+      // Passes (8 rows each): the first three quarters go to the warps in serpentine order (lists are sorted by length,
+      // so straight round robin would hand warp 0 the longest pass of every round), the rest is handed out by a
+      // shared counter so that the warps reach the barrier together.  The next pass's row and value chunks are
+      // requested before the current pass's entry loop (their L2 latency hides behind it).
       const int n_pass = (n_rows + kBatchRows - 1) / kBatchRows;
-      auto pass_of = [&](int round) { return round * kTileWarps + ((round & 1) ? kTileWarps - 1 - warp : warp); };
+      const int static_rounds = (n_pass / kTileWarps) * 3 / 4;
+      int round = 0;
+      auto next_pass = [&]() -> int {
+        int pass;
+        if (round < static_rounds) {
+          pass = round * kTileWarps + ((round & 1) ? kTileWarps - 1 - warp : warp);
+        } else {
+          unsigned v = 0;
+          if (lane == 0)
+            asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(v) : "r"((unsigned)__cvta_generic_to_shared(&sh.next_pass)) : "memory");
+          pass = static_rounds * kTileWarps + (int)__shfl_sync(kFull, v, 0);
+        }
+        ++round;
+        return pass;
+      };
       unsigned rl_n = 0u;
       float4 vA_n = zero4(), vB_n = zero4();
       auto request = [&](int pass) {
@@ -442,16 +508,22 @@ bwd_d32_tile_kernel(const D32Params p, const int grid_mode) {
           vB_n = C::load(vb + (ro + (first ^ 4)));
         }
       };
-      request(pass_of(0));
-      for (int round = 0; pass_of(round) < n_pass; ++round) {
+      int cur = next_pass();
+      request(cur);
+      while (cur < n_pass) {
         const unsigned rl = rl_n;
         const float4 vA = vA_n, vB = vB_n;
-        request(pass_of(round + 1));
+        cur = next_pass();
+        request(cur);
         const bool has = (rl >> 30) & 1u;
         const int c = (int)((rl >> 12) & 63u);
         const uint2* ep = sh.entries + ((rl >> 18) & 0xfffu);
         // lists are sorted by length: group 0 has the longest, group 7 the shortest of the pass
+#if MSDA_TILE_EXPERIMENT == 3      // timing experiment: no entry loop at all
+        const int cmax = 0, cmin = 0;
+#else
         const int cmax = __shfl_sync(kFull, c, 0), cmin = __shfl_sync(kFull, c, 28);
+#endif
         const unsigned ro = head + (unsigned)sh.rowtok[rl & 0xfffu] * 8u;
         float4 accA = zero4(), accB = zero4();
         int i = 0;
@@ -459,25 +531,30 @@ bwd_d32_tile_kernel(const D32Params p, const int grid_mode) {
         // together (lanes h = 0, 1 end up with the first, h = 2, 3 with the second)
         for (; i + 2 <= cmin; i += 2) {
           const uint2 e0 = ep[i], e1 = ep[i + 1];
-          const float4* g0 = Gl + ((e0.y >> 6) << 4);
-          const float4* g1 = Gl + ((e1.y >> 6) << 4);
-          const float4 a0 = g0[0], b0 = g0[4], a1 = g1[0], b1 = g1[4];
+          const unsigned q0 = (e0.y >> 6) << 3, q1 = (e1.y >> 6) << 3;
+#if MSDA_TILE_EXPERIMENT == 1      // timing experiment: half of the G-row reads
+          const float4 a0 = GA[q0], b0 = a0, a1 = GA[q1], b1 = a1;
+#else
+          const float4 a0 = GA[q0], b0 = GB[q0], a1 = GA[q1], b1 = GB[q1];
+#endif
           fma4(accA, __uint_as_float(e0.x), a0);
           fma4(accB, __uint_as_float(e0.x), b0);
           fma4(accA, __uint_as_float(e1.x), a1);
           fma4(accB, __uint_as_float(e1.x), b1);
+#if MSDA_TILE_EXPERIMENT != 2      // (2: timing experiment without the dot products)
           const float d0 = dot4(a0, vA) + dot4(b0, vB);
           const float d1 = dot4(a1, vA) + dot4(b1, vB);
           float r = ((h & 2) ? d1 : d0) + __shfl_xor_sync(kFull, (h & 2) ? d0 : d1, 2);
           r += __shfl_xor_sync(kFull, r, 1);
           if ((h & 1) == 0) sh.dbuf[(h & 2) ? e1.y : e0.y] = r;
+#endif
         }
         for (; i < cmax; ++i) {
           const bool act = i < c;
           uint2 e = make_uint2(0u, 0u);
           if (act) e = ep[i];
-          const float4* gq = Gl + ((e.y >> 6) << 4);
-          const float4 a0 = gq[0], b0 = gq[4];
+          const unsigned qq = (e.y >> 6) << 3;
+          const float4 a0 = GA[qq], b0 = GB[qq];
           fma4(accA, __uint_as_float(e.x), a0);
           fma4(accB, __uint_as_float(e.x), b0);
           float dp = dot4(a0, vA) + dot4(b0, vB);
@@ -491,18 +568,30 @@ bwd_d32_tile_kernel(const D32Params p, const int grid_mode) {
         }
       }
     }
+    {
+      const int Rz = sh.wbase[kTileL];
+      for (int i = t; i < Rz; i += kTileThreads) sh.off[i] = 0;
+      for (int i = t; i < kTileWarps * (kBins + 1); i += kTileThreads) (&sh.whist[0][0])[i] = 0;
+      if (t < kTileL * 3) (&sh.anchor_sum[0][0])[t] = 0;
+      if (t == 0) sh.n_left = 0;
+    }
     __syncthreads();                                                                   // B6
 
-    // ---- P3: per-sample gradients (cuh:156-158); clear the counters, decode the next unit ------------------------
+    // ---- P3: per-sample gradients (cuh:156-158); the next unit's grad_out rows are requested (G is free again).
+    // Everything is re-read from shared memory: nothing but the loop state lives across the row pass. ------------
     {
-      const float Wf = (float)Wl, Hf = (float)Hl;
+      const TileUnit un3 = sh.unit[slot_u];
+      if (more) request_grad_rows(sh, p, sh.unit[slot_u ^ 1], grid_mode, t);
+      if (t == 0) sh.next_pass = 0;
+      const int l3 = (t & 15) >> 2;
+      const float Wf = (float)sh.tab.W[l3], Hf = (float)sh.tab.H[l3];
+      const unsigned qb3 = (unsigned)un3.b * (unsigned)p.Lq;
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
-        const int q = tile_query((t >> 4) + 32 * i, ql_dy + 4 * i, ql_dx);
-        if (q >= 0) {
-          const unsigned gs = ((qbase + q) * M + m) * kTileLP + lp;
-          const float4 rc = sh.rec[t + kTileThreads * i];
-          const unsigned mk = __float_as_uint(rc.w);
+        const float4 rc = sh.rec[t + kTileThreads * i];
+        const unsigned mk = __float_as_uint(rc.w);
+        if (mk >> 5) {
+          const unsigned gs = ((qb3 + (mk >> 5) - 1u) * (unsigned)p.M + (unsigned)un3.m) * kTileLP + (t & 15);
           float pa = 0.f, px = 0.f, py = 0.f;
           if (mk & 15u) {
             const float4 d = reinterpret_cast<const float4*>(sh.dbuf)[t + kTileThreads * i];
@@ -517,18 +606,12 @@ bwd_d32_tile_kernel(const D32Params p, const int grid_mode) {
           st_stream(reinterpret_cast<float2*>(p.grad_loc) + gs, make_float2(px, py));
         }
       }
-      for (int i = t; i < R; i += kTileThreads) sh.off[i] = 0;
-      for (int i = t; i < kTileWarps * (kBins + 1); i += kTileThreads) (&sh.whist[0][0])[i] = 0;
-      if (t < kTileL * 3) (&sh.anchor_sum[0][0])[t] = 0;
-      if (t == 0) {
-        sh.n_left = 0;
-        if (u + gridDim.x < n_units) decode_unit(sh, grid_mode, u + gridDim.x, n_tiles, M);
-      }
     }
     __syncthreads();                                                                   // B7
   }
 }
 
+static_assert(2 * (sizeof(TileShared) + 1024) <= 228 * 1024, "two units per SM");
 inline size_t tile_smem_bytes() { return sizeof(TileShared); }
 
 }  // namespace msda
