@@ -74,7 +74,8 @@ int msda_fwd_bf16(const uint16_t *value, const int64_t *spatial_shapes, const in
 /* ---- backward --------------------------------------------------------------------------
  * Replaces ms_deformable_col2im_cuda<scalar_t> (cuh:956-1327) and its six kernels
  * (cuh:301-920).  grad_value is ACCUMULATED into and must be zero on entry (the reference
- * host code zero-fills it, .cu:121); grad_sampling_loc and grad_attn_weight are fully written. */
+ * host code zero-fills it, .cu:121); grad_sampling_loc and grad_attn_weight are fully written (as zeros when
+ * spatial_size is 0: no sample can land anywhere). */
 int msda_bwd_f32(const float *grad_output, const float *value, const int64_t *spatial_shapes,
                  const int64_t *level_start, const float *sampling_loc, const float *attn_weight,
                  int batch, int spatial_size, int num_heads, int channels, int num_levels,

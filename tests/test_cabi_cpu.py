@@ -171,3 +171,25 @@ def test_module_init_matches_reference_ring():
     assert float(m.sampling_offsets.weight.abs().max()) == 0.0
     assert float(m.attention_weights.weight.abs().max()) == 0.0 and float(m.attention_weights.bias.abs().max()) == 0.0
     assert float(m.value_proj.bias.abs().max()) == 0.0
+
+
+def test_host_plan_argument_validation():
+    """HostPlan hands bare pointers to the C ABI: dtype, contiguity and size are checked on the Python side
+    (no device needed: the plan object is built without its native handle)."""
+    import numpy as np
+    hp = cabi.HostPlan.__new__(cabi.HostPlan)
+    hp.dims = (2, 30, 2, 4, 2, 3, 2)       # N, S, M, D, L, Lq, P
+    hp._h = None
+    sizes = hp._sizes()
+    good = {"value": np.zeros(sizes["value"], np.float32), "shapes": np.zeros((2, 2), np.int64),
+            "lsi": np.zeros(2, np.int64), "loc": np.zeros(sizes["loc"], np.float32),
+            "aw": np.zeros(sizes["aw"], np.float32), "out": np.zeros(sizes["out"], np.float32)}
+    hp._validate(**good)
+    for name, bad in (("value", good["value"].astype(np.float64)), ("shapes", good["shapes"].astype(np.int32)),
+                      ("loc", np.zeros(2 * sizes["loc"], np.float32)[::2]), ("out", np.zeros(sizes["out"] - 1, np.float32))):
+        with pytest.raises(ValueError, match=name):
+            hp._validate(**{**good, name: bad})
+    ro = np.zeros(sizes["out"], np.float32)
+    ro.flags.writeable = False
+    with pytest.raises(ValueError, match="writeable"):
+        hp._validate(**{**good, "out": ro})

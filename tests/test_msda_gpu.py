@@ -976,3 +976,140 @@ def test_against_reference_cuda_kernels(dist, Lq):
     close(res["grad_aw"], ga_r.cpu().numpy(), GRAD_RTOL)
     # identical index decisions => identical touch pattern of grad_value
     assert np.array_equal(res["grad_value"] != 0, gv_r.cpu().numpy() != 0)
+
+
+# ------------------------------------------------------------------------------------------------
+# round 2: full-size gradients against the oracle for every BASELINE configuration
+# ------------------------------------------------------------------------------------------------
+
+def _oracle_one_sample(t, b, value_from_bf16=False):
+    """Oracle forward + backward for sample b of a full-size input set (the operator has no cross-sample term)."""
+    cpu = {k: (v[b:b + 1] if k in ("value", "loc", "aw", "grad_out") else v).cpu() for k, v in t.items()}
+    value = cpu["value"].float().numpy() if value_from_bf16 else cpu["value"].numpy()
+    return oracle(value, cpu["shapes"].numpy(), cpu["lsi"].numpy(), cpu["loc"].numpy(), cpu["aw"].numpy(),
+                  cpu["grad_out"].numpy())
+
+
+@pytest.mark.parametrize("name", ["c5_hires", "c5_hires_contended"])
+def test_full_size_c5_bf16_gradients_vs_oracle(name):
+    """BASELINE configs[4] (bf16 value, grad_value contention) at full size: all three gradients and the output of
+    one of the 8 images against the OpenMP oracle run on the values the kernel actually read."""
+    wl = WORKLOADS[name]
+    t, out, gv, gl, ga = _full_size(wl, kind="bf16", seed=3)
+    assert cabi.last_path(True) == "bwd_d32_tiles_bf16_f32acc"
+    b = 5
+    ref = _oracle_one_sample(t, b, value_from_bf16=True)
+    close(out[b:b + 1].cpu().numpy(), ref["out"], FWD_RTOL)
+    close(gl[b:b + 1].cpu().numpy(), ref["grad_loc"], GRAD_RTOL)
+    close(ga[b:b + 1].cpu().numpy(), ref["grad_aw"], GRAD_RTOL)
+    close(gv[b:b + 1].float().cpu().numpy(), ref["grad_value"], BF16_RTOL)     # rounded once to bf16
+    # which rows receive gradient is index work: exact
+    assert np.array_equal(gv[b:b + 1].float().cpu().numpy() != 0, ref["grad_value"] != 0)
+
+
+@pytest.mark.parametrize("tiles", [1, 0], ids=["direct", "auto"])
+def test_full_size_c5_f32_contended_grad_value(tiles):
+    """The contended distribution in fp32 through both backward families (tolerance of the fp32 path)."""
+    wl = WORKLOADS["c5_hires_contended"]
+    with Paths(0, 0, 1, tiles, 1):
+        t, out, gv, gl, ga = _full_size(wl, kind="f32", seed=4)
+        assert cabi.last_path(True) == ("bwd_d32_f32" if tiles == 1 else "bwd_d32_tiles_f32")
+    ref = _oracle_one_sample(t, 2)
+    close(gv[2:3].cpu().numpy(), ref["grad_value"], GRAD_RTOL)
+    close(gl[2:3].cpu().numpy(), ref["grad_loc"], GRAD_RTOL)
+
+
+@pytest.mark.parametrize("name,b", [("c3_arctic_encoder", 17), ("c3_arctic_decoder", 30), ("c4_dino_decoder", 1),
+                                    ("c4_dino_decoder_train", 0)])
+def test_full_size_c3_c4_grad_value_vs_oracle(name, b):
+    wl = WORKLOADS[name]
+    t, out, gv, gl, ga = _full_size(wl, seed=5)
+    ref = _oracle_one_sample(t, b)
+    close(out[b:b + 1].cpu().numpy(), ref["out"], FWD_RTOL)
+    close(gv[b:b + 1].cpu().numpy(), ref["grad_value"], GRAD_RTOL)
+    close(gl[b:b + 1].cpu().numpy(), ref["grad_loc"], GRAD_RTOL)
+    close(ga[b:b + 1].cpu().numpy(), ref["grad_aw"], GRAD_RTOL)
+
+
+def test_tile_backward_when_its_windows_miss():
+    """Encoder-shaped call (Lq == S picks the tile backward) whose locations have nothing to do with the query
+    grid: every corner misses the unit's windows, the row table overflows and the single-thread path serves
+    the rest.  Slow by construction, but it must still be right."""
+    wl = Workload("miss", 1, ((60, 70), (30, 35), (24, 25), (22, 23)), 60 * 70 + 30 * 35 + 24 * 25 + 22 * 23,
+                  loc_dist="uniform")
+    x = np_inputs(wl, 31)
+    with Paths(0, 0, 1, 0, 1):
+        res = run_cabi("f32", x["value"], x["shapes"], x["lsi"], x["loc"], x["aw"], x["grad_out"])
+    assert res["bwd_path"] == "bwd_d32_tiles_f32"
+    check_all(res, oracle(x["value"], x["shapes"], x["lsi"], x["loc"], x["aw"], x["grad_out"]))
+
+
+def test_backward_with_no_value_tokens_writes_zero_gradients():
+    """S == 0: msda_bwd_* promise grad_sampling_loc / grad_attn_weight 'fully written' (include/msda_b200.h)."""
+    N, M, D, L, Lq, P = 2, 8, 32, 4, 5, 4
+    sh = torch.zeros(L, 2, dtype=torch.long, device="cuda")
+    ls = torch.zeros(L, dtype=torch.long, device="cuda")
+    lo = torch.rand(N, Lq, M, L, P, 2, device="cuda")
+    a = torch.rand(N, Lq, M, L, P, device="cuda")
+    g = torch.randn(N, Lq, M * D, device="cuda")
+    v = torch.zeros(1, device="cuda")
+    gl = torch.full_like(lo, float("nan"))
+    ga = torch.full_like(a, float("nan"))
+    cabi.backward("f32", g.data_ptr(), v.data_ptr(), sh.data_ptr(), ls.data_ptr(), lo.data_ptr(), a.data_ptr(),
+                  (N, 0, M, D, L, Lq, P), v.data_ptr(), gl.data_ptr(), ga.data_ptr(),
+                  torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert float(gl.abs().max()) == 0 and float(ga.abs().max()) == 0
+
+
+def test_stale_cuda_error_is_not_blamed_on_the_operator():
+    """A non-sticky error left by an earlier caller (here: an impossible allocation) must not fail the next
+    operator call -- and must be gone afterwards."""
+    import ctypes
+    g = np.load(GOLDEN[IDS.index("d32_m8_l4_p4")])
+    v, lo, a = dev(g["value"]), dev(g["loc"]), dev(g["aw"])
+    sh, ls = dev(g["shapes"].astype(np.int64)), dev(g["lsi"].astype(np.int64))
+    N, S, M, D = v.shape
+    _, Lq, _, L, P, _ = lo.shape
+    out = torch.empty(N, Lq, M * D, device="cuda")
+    torch.cuda.synchronize()
+    rt = ctypes.CDLL("libcudart.so.12")
+    rt.cudaMalloc.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_size_t]
+    ptr = ctypes.c_void_p()
+    assert rt.cudaMalloc(ctypes.byref(ptr), ctypes.c_size_t(1 << 62)) != 0      # leaves cudaErrorMemoryAllocation behind
+    cabi.forward("f32", v.data_ptr(), sh.data_ptr(), ls.data_ptr(), lo.data_ptr(), a.data_ptr(),
+                 (N, S, M, D, L, Lq, P), out.data_ptr(), torch.cuda.current_stream().cuda_stream)   # raises on rc != 0
+    torch.cuda.synchronize()
+    close(out.cpu().numpy(), g["out"], FWD_RTOL)
+
+
+def test_module_half_precision_branch():
+    """models/dino/ops/modules/ms_deform_attn.py:124-131: a half-precision module upcasts value / locations / weights
+    to fp32 around the operator and casts the result back."""
+    from uvhand_b200.modules import MSDeformAttn
+    torch.manual_seed(9)
+    levels = ((12, 17), (6, 9), (3, 5), (2, 3))
+    shapes = torch.as_tensor(levels, dtype=torch.long).cuda()
+    lsi = torch.cat((shapes.new_zeros((1,)), shapes.prod(1).cumsum(0)[:-1]))
+    S = int(shapes.prod(1).sum())
+    N, Lq = 2, 23
+    mod32 = MSDeformAttn(256, 4, 8, 4).cuda()
+    with torch.no_grad():
+        mod32.sampling_offsets.weight.normal_(0, 0.02)
+        mod32.attention_weights.weight.normal_(0, 0.1)
+    mod16 = MSDeformAttn(256, 4, 8, 4).cuda()
+    mod16.load_state_dict(mod32.state_dict())
+    mod16 = mod16.half()
+    query = torch.randn(N, Lq, 256, device="cuda")
+    feat = torch.randn(N, S, 256, device="cuda")
+    refp = torch.rand(N, Lq, 4, 2, device="cuda")
+    q16 = query.half().requires_grad_(True)
+    f16 = feat.half().requires_grad_(True)
+    out16 = mod16(q16, refp.half(), f16, shapes, lsi, None)
+    assert out16.dtype == torch.float16
+    assert cabi.last_path(False) in ("fwd_d32_f32", "fwd_d32_split_f32")          # the operator itself ran in fp32
+    out16.float().sum().backward()
+    assert q16.grad.dtype == torch.float16 and f16.grad.dtype == torch.float16
+    out32 = mod32(query, refp, feat, shapes, lsi, None)
+    assert torch.allclose(out16.float(), out32, rtol=2e-2, atol=2e-2)
+    assert torch.isfinite(q16.grad.float()).all() and torch.isfinite(f16.grad.float()).all()

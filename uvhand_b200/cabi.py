@@ -166,17 +166,44 @@ class HostPlan:
     def _p(a):
         return a.ctypes.data_as(c_void_p)
 
+    def _sizes(self):
+        N, S, M, D, L, Lq, P = self.dims
+        n_aw = N * Lq * M * L * P
+        return {"value": N * S * M * D, "shapes": 2 * L, "lsi": L, "loc": 2 * n_aw, "aw": n_aw,
+                "grad_out": N * Lq * M * D, "out": N * Lq * M * D, "gv": N * S * M * D, "gl": 2 * n_aw, "ga": n_aw}
+
+    def _validate(self, **arrays):
+        """The C ABI takes bare pointers: a wrong dtype, a strided view or a short buffer would be read / overrun
+        silently, so every array is checked against the plan here."""
+        import numpy as np
+        sizes = self._sizes()
+        for name, a in arrays.items():
+            want = np.int64 if name in ("shapes", "lsi") else np.float32
+            if not isinstance(a, np.ndarray) or a.dtype != want:
+                raise ValueError(f"HostPlan: `{name}` must be a numpy array of {np.dtype(want).name}")
+            if not a.flags["C_CONTIGUOUS"]:
+                raise ValueError(f"HostPlan: `{name}` must be C-contiguous")
+            if a.size != sizes[name]:
+                raise ValueError(f"HostPlan: `{name}` has {a.size} elements, the plan needs {sizes[name]}")
+            if name in ("out", "gv", "gl", "ga") and not a.flags["WRITEABLE"]:
+                raise ValueError(f"HostPlan: `{name}` must be writeable")
+
     def forward(self, value, shapes, lsi, loc, aw, out):
+        self._validate(value=value, shapes=shapes, lsi=lsi, loc=loc, aw=aw, out=out)
         check(lib().msda_host_fwd_f32(self._h, self._p(value), self._p(shapes), self._p(lsi), self._p(loc),
                                       self._p(aw), self._p(out)), "msda_host_fwd_f32")
 
     def forward_backward(self, value, shapes, lsi, loc, aw, grad_out, out, gv, gl, ga):
+        self._validate(value=value, shapes=shapes, lsi=lsi, loc=loc, aw=aw, grad_out=grad_out, out=out, gv=gv, gl=gl,
+                       ga=ga)
         check(lib().msda_host_fwd_bwd_f32(self._h, self._p(value), self._p(shapes), self._p(lsi), self._p(loc),
                                           self._p(aw), self._p(grad_out), self._p(out), self._p(gv),
                                           self._p(gl), self._p(ga)), "msda_host_fwd_bwd_f32")
 
 
 def host_register(arr) -> None:
+    if not arr.flags["C_CONTIGUOUS"]:
+        raise ValueError("host_register: array must be C-contiguous")
     check(lib().msda_host_register(arr.ctypes.data_as(c_void_p), arr.nbytes), "msda_host_register")
 
 

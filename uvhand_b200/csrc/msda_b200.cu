@@ -80,9 +80,25 @@ void register_extents(const void* value, size_t value_bytes, const void* gv, siz
 #endif
 }
 
+// A stale, non-sticky error left behind by the host framework or an earlier caller must not be reported as this
+// call's: every entry point that launches clears the error state first (begin_call) and reports only what its own
+// launches produced (finish_launch).
+void begin_call() { cudaGetLastError(); }
+
 int finish_launch(int n_launched) {
   g_launches.fetch_add(n_launched, std::memory_order_relaxed);
   const cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? MSDA_OK : (int)e;
+}
+
+// Backward with no value tokens / levels / points: every sample contributes nothing, so the two gradients that the
+// header promises to be "fully written" are written as zeros (grad_value stays as the caller zeroed it).
+int zero_sample_grads(void* gl, void* ga, size_t elem, int N, int Lq, int M, int L, int P, cudaStream_t st) {
+  const size_t n = (size_t)N * Lq * M * L * P;
+  if (n == 0) return MSDA_OK;
+  if (!gl || !ga) return MSDA_ERR_NULL_POINTER;
+  cudaError_t e = cudaMemsetAsync(gl, 0, elem * n * 2, st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(ga, 0, elem * n, st);
   return e == cudaSuccess ? MSDA_OK : (int)e;
 }
 
@@ -140,6 +156,7 @@ constexpr size_t kSplitSmem = (size_t)kD32Warps * kMaxLPD32 * 16;
 
 template <typename VT, bool kFuse = false>
 int launch_fwd_d32(D32Params& p, cudaStream_t st, bool* split = nullptr, bool* wide = nullptr) {
+  begin_call();
   const int LP = p.L * p.P;
   p.n_items = (long long)p.N * p.Lq * p.M;
   const bool sp = use_split(p.n_items, MSDA_FWD_MINB, false);
@@ -179,6 +196,7 @@ int launch_fwd_d32(D32Params& p, cudaStream_t st, bool* split = nullptr, bool* w
 
 template <typename VT, typename GT, bool kFuse = false>
 int launch_bwd_d32(D32Params& p, cudaStream_t st, bool* split = nullptr) {
+  begin_call();
   const int LP = p.L * p.P;
   p.n_items = (long long)p.N * p.Lq * p.M;
   const bool sp = !kFuse && use_split(p.n_items, MSDA_BWD_MINB, true);
@@ -221,6 +239,7 @@ bool use_tiles(const D32Params& p) {
 
 template <typename VT, typename GT>
 int launch_bwd_tiles(D32Params& p, cudaStream_t st) {
+  begin_call();
   const int grid_mode = p.Lq == p.S ? 1 : 0;
   auto kernel = bwd_d32_tile_kernel<VT, GT>;
 #if MSDA_TILE_EXPERIMENT == 4      // timing experiment: one unit per SM (how much do two resident units overlap?)
@@ -252,6 +271,7 @@ int launch_bwd_tiles(D32Params& p, cudaStream_t st) {
 template <typename T>
 int fwd_any(const T* value, const int64_t* shapes, const int64_t* lsi, const T* loc, const T* aw,
             int N, int S, int M, int D, int L, int Lq, int P, T* out, cudaStream_t st) {
+  begin_call();
   const Dims d{N, S, M, D, L, Lq, P};
   const long long n_items = (long long)N * Lq * M;
   register_extents(value, (size_t)N * S * M * D * sizeof(T), nullptr, 0, st);
@@ -263,6 +283,7 @@ template <typename T>
 int bwd_any(const T* go, const T* value, const int64_t* shapes, const int64_t* lsi, const T* loc,
             const T* aw, int N, int S, int M, int D, int L, int Lq, int P, T* gv, T* gl, T* ga,
             cudaStream_t st) {
+  begin_call();
   const Dims d{N, S, M, D, L, Lq, P};
   const long long n_items = (long long)N * Lq * M;
   register_extents(value, (size_t)N * S * M * D * sizeof(T), gv, (size_t)N * S * M * D * sizeof(T), st);
@@ -436,7 +457,8 @@ int msda_bwd_f32(const float* go, const float* value, const int64_t* shapes, con
                  float* gv, float* gl, float* ga, void* stream) {
   int rc = check_dims(N, S, M, D, L, Lq, P);
   if (rc) return rc;
-  if (nothing_to_do(N, M, D, Lq) || L == 0 || P == 0 || S == 0) return MSDA_OK;
+  if (nothing_to_do(N, M, D, Lq) || L == 0 || P == 0) return MSDA_OK;
+  if (S == 0) return zero_sample_grads(gl, ga, sizeof(float), N, Lq, M, L, P, (cudaStream_t)stream);
   if (!go || !value || !shapes || !lsi || !loc || !aw || !gv || !gl || !ga) return MSDA_ERR_NULL_POINTER;
   if (!aligned(go, 4) || !aligned(value, 4) || !aligned(loc, 4) || !aligned(aw, 4) || !aligned(gv, 4) ||
       !aligned(gl, 4) || !aligned(ga, 4) || !aligned(shapes, 8) || !aligned(lsi, 8))
@@ -468,7 +490,8 @@ int msda_bwd_f64(const double* go, const double* value, const int64_t* shapes, c
                  double* gv, double* gl, double* ga, void* stream) {
   int rc = check_dims(N, S, M, D, L, Lq, P);
   if (rc) return rc;
-  if (nothing_to_do(N, M, D, Lq) || L == 0 || P == 0 || S == 0) return MSDA_OK;
+  if (nothing_to_do(N, M, D, Lq) || L == 0 || P == 0) return MSDA_OK;
+  if (S == 0) return zero_sample_grads(gl, ga, sizeof(double), N, Lq, M, L, P, (cudaStream_t)stream);
   if (!go || !value || !shapes || !lsi || !loc || !aw || !gv || !gl || !ga) return MSDA_ERR_NULL_POINTER;
   if (!aligned(go, 8) || !aligned(value, 8) || !aligned(loc, 8) || !aligned(aw, 8) || !aligned(gv, 8) ||
       !aligned(gl, 8) || !aligned(ga, 8) || !aligned(shapes, 8) || !aligned(lsi, 8))
@@ -483,7 +506,8 @@ int msda_bwd_bf16(const float* go, const uint16_t* value, const int64_t* shapes,
                   uint16_t* gv, float* gl, float* ga, float* gv_scratch, void* stream) {
   int rc = check_dims(N, S, M, D, L, Lq, P);
   if (rc) return rc;
-  if (nothing_to_do(N, M, D, Lq) || L == 0 || P == 0 || S == 0) return MSDA_OK;
+  if (nothing_to_do(N, M, D, Lq) || L == 0 || P == 0) return MSDA_OK;
+  if (S == 0) return zero_sample_grads(gl, ga, sizeof(float), N, Lq, M, L, P, (cudaStream_t)stream);
   if (!go || !value || !shapes || !lsi || !loc || !aw || !gv || !gl || !ga) return MSDA_ERR_NULL_POINTER;
   if (!d32_eligible(S, M, D, L, P)) return MSDA_ERR_UNSUPPORTED;
   if (!aligned(go, 16) || !aligned(value, 8) || !aligned(gv, 8) || !aligned(loc, 8) || !aligned(aw, 4) ||
@@ -557,7 +581,8 @@ int msda_fused_bwd_f32(const float* go, const float* value, const int64_t* shape
                        float* g_ref, void* stream) {
   int rc = check_dims(N, S, M, D, L, Lq, P);
   if (rc) return rc;
-  if (nothing_to_do(N, M, D, Lq) || L == 0 || P == 0 || S == 0) return MSDA_OK;
+  if (nothing_to_do(N, M, D, Lq) || L == 0 || P == 0) return MSDA_OK;
+  if (S == 0) return zero_sample_grads(g_offsets, g_logits, sizeof(float), N, Lq, M, L, P, (cudaStream_t)stream);
   if (!go || !value || !shapes || !lsi || !ref || !offsets || !logits || !gv || !g_offsets || !g_logits)
     return MSDA_ERR_NULL_POINTER;
   if (!d32_eligible(S, M, D, L, P)) return MSDA_ERR_UNSUPPORTED;
@@ -584,6 +609,7 @@ int msda_sample_index_f32(const int64_t* shapes, const float* loc, int N, int Lq
   long long blocks = (n + 255) / 256;
   const long long cap = (long long)sm_count() * 32;
   if (blocks > cap) blocks = cap;
+  begin_call();
   sample_index_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(shapes, loc, n, L, P, h_low, w_low, mask);
   return finish_launch(1);
 }
