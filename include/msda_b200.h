@@ -127,6 +127,19 @@ int msda_fused_bwd_f32(const float *grad_output, const float *value, const int64
                        float *grad_value, float *grad_sampling_offsets, float *grad_attn_logits,
                        float *grad_reference_points, void *stream);
 
+/* ---- value producer side ------------------------------------
+ * MSDeformAttn.forward builds the operator's `value` as value_proj(x).masked_fill(padding_mask[..., None], 0)
+ * (models/ops/modules/ms_deform_attn.py:96-98).  For the bf16-value kernels these do the mask and the cast in ONE
+ * pass over the projection's fp32 output, and the matching backward:
+ *   msda_value_pack_bf16        value_bf16[r, :] = padding_mask[r] ? 0 : bf16(value_f32[r, :])
+ *   msda_value_unpack_grad_bf16 grad_f32[r, :]   = padding_mask[r] ? 0 : float(grad_bf16[r, :])
+ * rows = batch * spatial_size tokens; cols = num_heads * channels (a multiple of 8); padding_mask: one byte per row,
+ * non-zero = padded token, or NULL for no mask.  No reference analogue (the reference has no bf16 mode). */
+int msda_value_pack_bf16(const float *value_f32, const uint8_t *padding_mask, int64_t rows, int cols,
+                         uint16_t *value_bf16, void *stream);
+int msda_value_unpack_grad_bf16(const uint16_t *grad_bf16, const uint8_t *padding_mask, int64_t rows, int cols,
+                                float *grad_f32, void *stream);
+
 /* ---- parity probe ----------------------------------------------------------------------
  * Dumps, for every (n, q, m, l, p), what the kernels' shared sample-geometry routine decides:
  * floor of the pixel coordinate and the corner mask (bit0..3 = corner v1..v4 inside the level,

@@ -823,10 +823,11 @@ def test_module_fused_prologue_equals_unfused(ref_dim):
     lsi = torch.cat((shapes.new_zeros((1,)), shapes.prod(1).cumsum(0)[:-1]))
     S = int(shapes.prod(1).sum())
     N, Lq = 2, 41
-    plain = MSDeformAttn(256, 4, 8, 4).cuda()
+    plain = MSDeformAttn(256, 4, 8, 4, fuse_prologue=False).cuda()
     with torch.no_grad():
         plain.sampling_offsets.weight.normal_(0, 0.02)
         plain.attention_weights.weight.normal_(0, 0.1)
+    assert MSDeformAttn(256, 4, 8, 4).fuse_prologue          # the default (round 2)
     fused = MSDeformAttn(256, 4, 8, 4, fuse_prologue=True).cuda()
     fused.load_state_dict(plain.state_dict())
     pad = torch.zeros(N, S, dtype=torch.bool, device="cuda")
@@ -1113,3 +1114,92 @@ def test_module_half_precision_branch():
     out32 = mod32(query, refp, feat, shapes, lsi, None)
     assert torch.allclose(out16.float(), out32, rtol=2e-2, atol=2e-2)
     assert torch.isfinite(q16.grad.float()).all() and torch.isfinite(f16.grad.float()).all()
+
+
+def test_value_pack_bf16_equals_torch_mask_then_cast():
+    """one pass for padding mask + bf16 cast, and its backward, bit for bit what the torch
+    sequence masked_fill -> to(bfloat16) (and its autograd) gives."""
+    from uvhand_b200.functions import ValueToBF16Function
+    torch.manual_seed(3)
+    N, S, C = 3, 517, 256
+    v = torch.randn(N, S, C, device="cuda")
+    mask = torch.rand(N, S, device="cuda") < 0.2
+    for m in (mask, None):
+        a = v.clone().requires_grad_(True)
+        b = v.clone().requires_grad_(True)
+        out = ValueToBF16Function.apply(a, m)
+        want = (b.masked_fill(m[..., None], 0.0) if m is not None else b).to(torch.bfloat16)
+        assert out.dtype == torch.bfloat16 and torch.equal(out, want)
+        g = torch.randn(N, S, C, device="cuda").to(torch.bfloat16)
+        out.backward(g)
+        want.backward(g)
+        assert torch.equal(a.grad, b.grad)
+
+
+@pytest.mark.parametrize("ref_dim", [2, 4])
+def test_module_bf16_value_path(ref_dim):
+    """MSDeformAttn(value_dtype=bfloat16): value written once as bf16 (mask folded in), bf16-value kernels, fp32
+    everything else -- against the fp32 module with the operator replaced by the port of the reference CPU path,
+    at the bf16 tolerance of BASELINE.json (1e-2)."""
+    from oracle.grid_sample_port import msda_grid_sample
+    from uvhand_b200.modules import MSDeformAttn
+    torch.manual_seed(6)
+    levels = ((12, 17), (6, 9), (3, 5), (2, 3))
+    shapes = torch.as_tensor(levels, dtype=torch.long).cuda()
+    lsi = torch.cat((shapes.new_zeros((1,)), shapes.prod(1).cumsum(0)[:-1]))
+    S = int(shapes.prod(1).sum())
+    N, Lq = 2, 37
+    mod = MSDeformAttn(256, 4, 8, 4, value_dtype=torch.bfloat16).cuda()
+    with torch.no_grad():
+        mod.sampling_offsets.weight.normal_(0, 0.02)
+        mod.attention_weights.weight.normal_(0, 0.1)
+    query = torch.randn(N, Lq, 256, device="cuda", requires_grad=True)
+    feat = torch.randn(N, S, 256, device="cuda", requires_grad=True)
+    refp = torch.rand(N, Lq, 4, ref_dim, device="cuda")
+    if ref_dim == 4:
+        refp[..., 2:] *= 0.3
+    pad = torch.zeros(N, S, dtype=torch.bool, device="cuda")
+    pad[:, -5:] = True
+    n0 = cabi.launch_count()
+    out = mod(query, refp, feat, shapes, lsi, pad)
+    assert out.dtype == torch.float32 and "bf16" in cabi.last_path(False)
+    out.sum().backward()
+    torch.cuda.synchronize()
+    assert "bf16" in cabi.last_path(True)
+    assert cabi.launch_count() - n0 == 5       # pack, forward, backward + final rounding, unpack
+    gq, gf = query.grad.clone(), feat.grad.clone()
+    query.grad = feat.grad = None
+    value = mod.value_proj(feat).masked_fill(pad[..., None], 0.0).view(N, S, 8, 32)
+    off = mod.sampling_offsets(query).view(N, Lq, 8, 4, 4, 2)
+    w = torch.softmax(mod.attention_weights(query).view(N, Lq, 8, 16), -1).view(N, Lq, 8, 4, 4)
+    loc = MSDeformAttn._sampling_locations(refp, off, shapes)
+    out2 = mod.output_proj(msda_grid_sample(value, levels, loc, w))
+    out2.sum().backward()
+    tol = BF16_RTOL
+    assert torch.allclose(out, out2, rtol=tol, atol=tol * float(out2.abs().max()))
+    assert torch.allclose(gq, query.grad, rtol=tol, atol=tol * float(query.grad.abs().max()))
+    assert torch.allclose(gf, feat.grad, rtol=tol, atol=tol * float(feat.grad.abs().max()))
+    assert float(gf[:, -5:].abs().max()) == 0          # padded tokens receive no gradient
+
+
+@pytest.mark.parametrize("case", [
+    (2, 8, 735, ((20, 27), (10, 14), (5, 7), (3, 4)), 0.4),        # small pyramid windowed whole, linear tiles, refs mostly inside
+    (1, 8, 40 * 57 + 20 * 29 + 10 * 15 + 5 * 8, MID_LEVELS, 1.3),  # Lq == S: 8x8 pixel tiles, windows, leftovers, refs outside
+    (2, 3, 200, ((9, 13), (5, 7), (3, 4), (2, 2)), 1.0),           # 3 heads
+], ids=["whole", "grid", "m3"])
+def test_fused_prologue_through_the_tile_backward(case):
+    """msda_fused_bwd_f32 dispatched to the on-chip-combining backward (softmax / location prologue in its geometry
+    phase, their backward in its epilogue), against the unfused restatement."""
+    N, M, Lq, levels, spread = case
+    x = _fused_inputs(N, M, 4, 4, Lq, levels, seed=23, ref_spread=spread)
+    loc, a, ref = _fused_reference(x)
+    with Paths(0, 0, 1, 2, 1):
+        res, _ = _run_fused(x)
+        assert res["bwd_path"] == "bwd_d32_tiles_fused_f32"
+        res2, _ = _run_fused(x, want_ref=False)
+    close(res["out"], ref["out"], FWD_RTOL)
+    close(res["grad_value"], ref["grad_value"], GRAD_RTOL)
+    close(res["grad_off"], ref["grad_off"], GRAD_RTOL)
+    close(res["grad_logits"], ref["grad_logits"], GRAD_RTOL)
+    close(res["grad_ref"], ref["grad_ref"], GRAD_RTOL)
+    assert np.array_equal(res2["grad_off"], res["grad_off"]) and res2["grad_ref"] is None

@@ -237,11 +237,11 @@ bool use_tiles(const D32Params& p) {
   return (p.Lq == p.S || p.S <= kWholeMaxRows) && units >= 2ll * sm_count();
 }
 
-template <typename VT, typename GT>
+template <typename VT, typename GT, bool kFuse = false>
 int launch_bwd_tiles(D32Params& p, cudaStream_t st) {
   begin_call();
   const int grid_mode = p.Lq == p.S ? 1 : 0;
-  auto kernel = bwd_d32_tile_kernel<VT, GT>;
+  auto kernel = bwd_d32_tile_kernel<VT, GT, kFuse>;
 #if MSDA_TILE_EXPERIMENT == 4      // timing experiment: one unit per SM (how much do two resident units overlap?)
   const size_t smem = tile_smem_bytes() + 100 * 1024;
 #else
@@ -594,8 +594,45 @@ int msda_fused_bwd_f32(const float* go, const float* value, const int64_t* shape
   p.value = value; p.shapes = shapes; p.lsi = lsi; p.loc = offsets; p.aw = logits; p.ref = ref; p.grad_out = go;
   p.grad_value = gv; p.grad_loc = g_offsets; p.grad_aw = g_logits; p.grad_ref = g_ref;
   p.N = N; p.S = S; p.M = M; p.L = L; p.Lq = Lq; p.P = P;
+  if (use_tiles(p)) {
+    g_last_path[1] = "bwd_d32_tiles_fused_f32";
+    return launch_bwd_tiles<float, float, true>(p, (cudaStream_t)stream);
+  }
   g_last_path[1] = "bwd_d32_fused_f32";
   return launch_bwd_d32<float, float, true>(p, (cudaStream_t)stream);
+}
+
+// ---- value producer side ------------------------------------------------
+
+static int value_pack_common(const void* src, const uint8_t* mask, void* dst, int64_t rows, int cols, bool pack,
+                             void* stream) {
+  if (rows < 0 || cols < 0) return MSDA_ERR_BAD_DIMS;
+  if (rows == 0 || cols == 0) return MSDA_OK;
+  if (!src || !dst) return MSDA_ERR_NULL_POINTER;
+  if (cols % 8 != 0) return MSDA_ERR_UNSUPPORTED;
+  if (!aligned(src, 16) || !aligned(dst, 16)) return MSDA_ERR_MISALIGNED;
+  const long long n8 = (long long)rows * (cols / 8);
+  long long blocks = (n8 + 255) / 256;
+  const long long cap = (long long)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  begin_call();
+  if (pack)
+    value_pack_bf16_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(src), mask,
+                                                                         reinterpret_cast<uint4*>(dst), n8, cols / 8);
+  else
+    value_unpack_grad_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint4*>(src), mask,
+                                                                           reinterpret_cast<float4*>(dst), n8, cols / 8);
+  return finish_launch(1);
+}
+
+int msda_value_pack_bf16(const float* value_f32, const uint8_t* padding_mask, int64_t rows, int cols,
+                         uint16_t* value_bf16, void* stream) {
+  return value_pack_common(value_f32, padding_mask, value_bf16, rows, cols, true, stream);
+}
+
+int msda_value_unpack_grad_bf16(const uint16_t* grad_bf16, const uint8_t* padding_mask, int64_t rows, int cols,
+                                float* grad_f32, void* stream) {
+  return value_pack_common(grad_bf16, padding_mask, grad_f32, rows, cols, false, stream);
 }
 
 // ---- parity probe -------------------------------------------------------------------------

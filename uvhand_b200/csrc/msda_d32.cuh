@@ -693,4 +693,43 @@ __global__ void __launch_bounds__(256) f32_to_bf16_kernel(const float4* __restri
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Value producer side: the module's value path is
+//     value = value_proj(x); value = value.masked_fill(padding_mask[..., None], 0)        (ms_deform_attn.py:96-98)
+// followed, for bf16 kernels, by a cast.  These two kernels do mask + cast in ONE pass over the projection's fp32
+// output (read 4 B, write 2 B per element; the torch sequence reads/writes 14 B), and the matching backward
+// (bf16 grad_value -> fp32 gradient of the projection output, masked rows zero).
+// rows = N*S tokens, `cols` channels per token (multiple of 8), mask[row] != 0 -> padded token.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) value_pack_bf16_kernel(const float4* __restrict__ src, const uint8_t* __restrict__ mask,
+                                                              uint4* __restrict__ dst, long long n_vec8, int vec8_per_row) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec8; i += (long long)gridDim.x * blockDim.x) {
+    uint4 o = make_uint4(0u, 0u, 0u, 0u);
+    if (!mask || !mask[i / vec8_per_row]) {
+      const float4 a = ld_stream(src + 2 * i), b = ld_stream(src + 2 * i + 1);
+      const __nv_bfloat162 p0 = __floats2bfloat162_rn(a.x, a.y), p1 = __floats2bfloat162_rn(a.z, a.w);
+      const __nv_bfloat162 p2 = __floats2bfloat162_rn(b.x, b.y), p3 = __floats2bfloat162_rn(b.z, b.w);
+      o.x = *reinterpret_cast<const unsigned*>(&p0); o.y = *reinterpret_cast<const unsigned*>(&p1);
+      o.z = *reinterpret_cast<const unsigned*>(&p2); o.w = *reinterpret_cast<const unsigned*>(&p3);
+    }
+    dst[i] = o;
+  }
+}
+
+__global__ void __launch_bounds__(256) value_unpack_grad_kernel(const uint4* __restrict__ src, const uint8_t* __restrict__ mask,
+                                                                float4* __restrict__ dst, long long n_vec8, int vec8_per_row) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec8; i += (long long)gridDim.x * blockDim.x) {
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    if (!mask || !mask[i / vec8_per_row]) {
+      const uint4 r = __ldg(src + i);
+      a.x = __uint_as_float(r.x << 16); a.y = __uint_as_float(r.x & 0xffff0000u);
+      a.z = __uint_as_float(r.y << 16); a.w = __uint_as_float(r.y & 0xffff0000u);
+      b.x = __uint_as_float(r.z << 16); b.y = __uint_as_float(r.z & 0xffff0000u);
+      b.z = __uint_as_float(r.w << 16); b.w = __uint_as_float(r.w & 0xffff0000u);
+    }
+    st_stream(dst + 2 * i, a);
+    st_stream(dst + 2 * i + 1, b);
+  }
+}
+
 }  // namespace msda

@@ -178,7 +178,10 @@ __device__ __noinline__ bool leftover_corner(TileShared& sh, int R, int row_m, f
   return true;
 }
 
-template <typename VT, typename GT>
+// kFuse: the fused-prologue operator (msda_fused_bwd_f32): `loc` holds raw sampling offsets, `aw` raw attention logits;
+// softmax and reference + offset / (W, H) happen in P1a (the same routines as the other fused kernels), their
+// backward in P3 (/root/reference/models/ops/modules/ms_deform_attn.py:100-108).
+template <typename VT, typename GT, bool kFuse = false>
 __global__ void __launch_bounds__(kTileThreads, 2)
 bwd_d32_tile_kernel(const D32Params p, const int grid_mode) {
   using C = Chunk<VT>;
@@ -269,9 +272,16 @@ bwd_d32_tile_kernel(const D32Params p, const int grid_mode) {
     for (int i = 0; i < 2; ++i) {
       const int q = tile_query((t >> 4) + 32 * i, ql_dy + 4 * i, ql_dx);
       msk[i] = 0; lh[i] = 0.f; lw[i] = 0.f; aw[i] = 0.f; h_low[i] = 0; w_low[i] = 0;
+      float a_raw = -INFINITY;
+      if (q >= 0) a_raw = sh.stage_aw[t + kTileThreads * i];
+      // fused: the 16 logits of a (query, head) sit in 16 consecutive lanes (absent queries pass -inf)
+      const float a = kFuse ? segment_softmax<kTileLP>(a_raw) : a_raw;
       if (q >= 0) {
-        const float2 xy = sh.stage_loc[t + kTileThreads * i];
-        const float a = sh.stage_aw[t + kTileThreads * i];
+        float2 xy = sh.stage_loc[t + kTileThreads * i];
+        if (kFuse) {
+          xy = fused_location(p, (long long)(qbase + q) * M + m, l, xy, Hl, Wl);
+          aw[i] = a;                  // the softmax backward needs the weight of rejected samples too
+        }
         SampleGeom<float> g;
         if (sample_geom<float>(xy.x, xy.y, Hl, Wl, g)) {
           msk[i] = g.mask | 16u;      // bit 4: accepted by the coarse test (a sample may have no valid corner)
@@ -590,7 +600,7 @@ bwd_d32_tile_kernel(const D32Params p, const int grid_mode) {
       for (int i = 0; i < 2; ++i) {
         const float4 rc = sh.rec[t + kTileThreads * i];
         const unsigned mk = __float_as_uint(rc.w);
-        if (mk >> 5) {
+        if (!kFuse && (mk >> 5)) {
           const unsigned gs = ((qb3 + (mk >> 5) - 1u) * (unsigned)p.M + (unsigned)un3.m) * kTileLP + (t & 15);
           float pa = 0.f, px = 0.f, py = 0.f;
           if (mk & 15u) {
@@ -602,8 +612,44 @@ bwd_d32_tile_kernel(const D32Params p, const int grid_mode) {
             px = (hh * (d2 - d1) + rc.x * (d4 - d3)) * rc.z * Wf;
             py = (hw * (d3 - d1) + rc.y * (d4 - d2)) * rc.z * Hf;
           }
-          st_stream(p.grad_aw + gs, pa);
-          st_stream(reinterpret_cast<float2*>(p.grad_loc) + gs, make_float2(px, py));
+          if (!kFuse) {
+            st_stream(p.grad_aw + gs, pa);
+            st_stream(reinterpret_cast<float2*>(p.grad_loc) + gs, make_float2(px, py));
+          }
+        }
+        if (kFuse) {
+          // (every lane takes part in the shuffles; absent queries carry zeros)
+          const bool live = (mk >> 5) != 0;
+          const float a = live ? rc.z : 0.f;
+          float pa = 0.f, px = 0.f, py = 0.f;
+          if (live && (mk & 15u)) {
+            const float4 d = reinterpret_cast<const float4*>(sh.dbuf)[t + kTileThreads * i];
+            const float d1 = (mk & 1u) ? d.x : 0.f, d2 = (mk & 2u) ? d.y : 0.f;
+            const float d3 = (mk & 4u) ? d.z : 0.f, d4 = (mk & 8u) ? d.w : 0.f;
+            const float hh = 1.f - rc.x, hw = 1.f - rc.y;
+            pa = hh * hw * d1 + hh * rc.y * d2 + rc.x * hw * d3 + rc.x * rc.y * d4;
+            px = (hh * (d2 - d1) + rc.x * (d4 - d3)) * a * Wf;
+            py = (hw * (d3 - d1) + rc.y * (d4 - d2)) * a * Hf;
+          }
+          // softmax backward over the 16 samples of the (query, head): d/d logit_s = a_s (ga_s - sum_j a_j ga_j)
+          float dot = a * pa;
+#pragma unroll
+          for (int o = 1; o < kTileLP; o <<= 1) dot += __shfl_xor_sync(kFull, dot, o);
+          // d/d reference point of (query, level) = sum over points (here) and heads (other units: atomics)
+          float rx = px, ry = py;
+          rx += __shfl_xor_sync(kFull, rx, 1); ry += __shfl_xor_sync(kFull, ry, 1);
+          rx += __shfl_xor_sync(kFull, rx, 2); ry += __shfl_xor_sync(kFull, ry, 2);
+          if (live) {
+            const unsigned q3 = qb3 + (mk >> 5) - 1u;
+            const unsigned gs = (q3 * (unsigned)p.M + (unsigned)un3.m) * kTileLP + (t & 15);
+            st_stream(p.grad_aw + gs, a * (pa - dot));
+            st_stream(reinterpret_cast<float2*>(p.grad_loc) + gs, make_float2(__fdiv_rn(px, Wf), __fdiv_rn(py, Hf)));
+            if (p.grad_ref && (t & 3) == 0) {
+              float* gr = p.grad_ref + ((size_t)q3 * kTileL + l3) * 2;
+              atomicAdd(gr, rx);
+              atomicAdd(gr + 1, ry);
+            }
+          }
         }
       }
     }

@@ -269,7 +269,44 @@ std::vector<at::Tensor> ms_deform_attn_fused_backward(const at::Tensor& value, c
   return {grad_value, grad_off, grad_logits, grad_ref};
 }
 
+// value producer side: mask + cast of the value projection's output in one pass
+namespace {
+const uint8_t* mask_ptr(const at::Tensor& value, const c10::optional<at::Tensor>& mask, int64_t rows) {
+  if (!mask.has_value() || !mask->defined()) return nullptr;
+  TORCH_CHECK(mask->is_cuda() && mask->device() == value.device() && mask->is_contiguous() && mask->numel() == rows &&
+                  (mask->scalar_type() == at::kBool || mask->scalar_type() == at::kByte),
+              "padding mask must be a contiguous bool/uint8 CUDA tensor with one entry per token");
+  return reinterpret_cast<const uint8_t*>(mask->data_ptr());
+}
+}  // namespace
+
+at::Tensor ms_deform_attn_value_to_bf16(const at::Tensor& value, const c10::optional<at::Tensor>& padding_mask) {
+  TORCH_CHECK(value.is_cuda(), "Not implemented on the CPU");
+  TORCH_CHECK(value.is_contiguous() && value.scalar_type() == at::kFloat && value.dim() >= 2, "value must be contiguous float32 [..., C]");
+  const int64_t cols = value.size(-1), rows = value.numel() / std::max<int64_t>(cols, 1);
+  const c10::cuda::CUDAGuard guard(value.device());
+  at::Tensor out = at::empty(value.sizes(), value.options().dtype(at::kBFloat16));
+  check_rc(msda_value_pack_bf16(value.data_ptr<float>(), mask_ptr(value, padding_mask, rows), rows, (int)cols,
+                                reinterpret_cast<uint16_t*>(out.data_ptr()), at::cuda::getCurrentCUDAStream().stream()),
+           "ms_deform_attn_value_to_bf16");
+  return out;
+}
+
+at::Tensor ms_deform_attn_value_grad_from_bf16(const at::Tensor& grad, const c10::optional<at::Tensor>& padding_mask) {
+  TORCH_CHECK(grad.is_cuda(), "Not implemented on the CPU");
+  TORCH_CHECK(grad.is_contiguous() && grad.scalar_type() == at::kBFloat16 && grad.dim() >= 2, "grad must be contiguous bfloat16 [..., C]");
+  const int64_t cols = grad.size(-1), rows = grad.numel() / std::max<int64_t>(cols, 1);
+  const c10::cuda::CUDAGuard guard(grad.device());
+  at::Tensor out = at::empty(grad.sizes(), grad.options().dtype(at::kFloat));
+  check_rc(msda_value_unpack_grad_bf16(reinterpret_cast<const uint16_t*>(grad.data_ptr()), mask_ptr(grad, padding_mask, rows),
+                                       rows, (int)cols, out.data_ptr<float>(), at::cuda::getCurrentCUDAStream().stream()),
+           "ms_deform_attn_value_grad_from_bf16");
+  return out;
+}
+
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+  m.def("ms_deform_attn_value_to_bf16", &ms_deform_attn_value_to_bf16, "mask + cast of the value projection output");
+  m.def("ms_deform_attn_value_grad_from_bf16", &ms_deform_attn_value_grad_from_bf16, "backward of value_to_bf16");
   m.def("ms_deform_attn_forward", &ms_deform_attn_forward, "ms_deform_attn_forward");
   m.def("ms_deform_attn_backward", &ms_deform_attn_backward, "ms_deform_attn_backward");
   // additions (not in the reference module)

@@ -1,1 +1,2 @@
-from .ms_deform_attn_func import MSDeformAttnFunction, MSDeformAttnFusedFunction, fused_supported  # noqa: F401
+from .ms_deform_attn_func import (MSDeformAttnFunction, MSDeformAttnFusedFunction, ValueToBF16Function,  # noqa: F401
+                                   bf16_value_mode, fused_supported)

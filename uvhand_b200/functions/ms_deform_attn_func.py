@@ -42,12 +42,29 @@ def get_bf16_value_mode() -> bool:
     return _bf16_value_mode
 
 
-def _kernel_value(value: torch.Tensor, sampling_locations: torch.Tensor) -> torch.Tensor:
+class bf16_value_mode:
+    """``with bf16_value_mode(True): ...`` -- scoped form of :func:`set_bf16_value_mode` (the mode in force when the
+    forward runs is remembered for that call's backward)."""
+
+    def __init__(self, enabled: bool = True):
+        self.enabled = bool(enabled)
+
+    def __enter__(self):
+        self.prev = get_bf16_value_mode()
+        set_bf16_value_mode(self.enabled)
+        return self
+
+    def __exit__(self, *exc):
+        set_bf16_value_mode(self.prev)
+        return False
+
+
+def _kernel_value(value: torch.Tensor, sampling_locations: torch.Tensor, native_bf16: bool) -> torch.Tensor:
     if value.dtype == torch.float32:
         return value
     if value.dtype == torch.float64 and sampling_locations.dtype == torch.float64:
         return value
-    if value.dtype == torch.bfloat16 and _bf16_value_mode and sampling_locations.dtype == torch.float32:
+    if value.dtype == torch.bfloat16 and native_bf16 and sampling_locations.dtype == torch.float32:
         return value
     return value.to(torch.float32)
 
@@ -57,8 +74,9 @@ class MSDeformAttnFunction(Function):
     def forward(ctx, value, value_spatial_shapes, value_level_start_index, sampling_locations,
                 attention_weights, im2col_step):
         ctx.im2col_step = im2col_step
+        ctx.native_bf16 = _bf16_value_mode
         output = MSDA.ms_deform_attn_forward(
-            _kernel_value(value, sampling_locations), value_spatial_shapes, value_level_start_index,
+            _kernel_value(value, sampling_locations, ctx.native_bf16), value_spatial_shapes, value_level_start_index,
             sampling_locations, attention_weights, ctx.im2col_step)
         # like the reference, the tensor as given (not the cast copy) is what is kept alive
         ctx.save_for_backward(value, value_spatial_shapes, value_level_start_index,
@@ -71,9 +89,26 @@ class MSDeformAttnFunction(Function):
         value, value_spatial_shapes, value_level_start_index, sampling_locations, attention_weights = \
             ctx.saved_tensors
         grad_value, grad_sampling_loc, grad_attn_weight = MSDA.ms_deform_attn_backward(
-            _kernel_value(value, sampling_locations), value_spatial_shapes, value_level_start_index,
+            _kernel_value(value, sampling_locations, ctx.native_bf16), value_spatial_shapes, value_level_start_index,
             sampling_locations, attention_weights, grad_output.contiguous(), ctx.im2col_step)
         return grad_value, None, None, grad_sampling_loc, grad_attn_weight, None
+
+
+class ValueToBF16Function(Function):
+    """value_proj output (float32 [N, S, C]) -> the bf16 ``value`` the kernels gather from, with the padding mask
+    applied in the same pass (/root/reference/models/ops/modules/ms_deform_attn.py:96-98 does
+    ``masked_fill`` as a pass of its own, and a bf16 mode would add a cast pass).  SURVEY.md 8f rank 2."""
+
+    @staticmethod
+    def forward(ctx, value, padding_mask):
+        mask = None if padding_mask is None else padding_mask.contiguous()
+        ctx.mask = mask
+        return MSDA.ms_deform_attn_value_to_bf16(value.contiguous(), mask)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad):
+        return MSDA.ms_deform_attn_value_grad_from_bf16(grad.contiguous(), ctx.mask), None
 
 
 class MSDeformAttnFusedFunction(Function):

@@ -22,7 +22,14 @@ from torch import nn
 
 import os
 
-from ..functions.ms_deform_attn_func import MSDeformAttnFunction, MSDeformAttnFusedFunction, fused_supported
+from ..functions.ms_deform_attn_func import (MSDeformAttnFunction, MSDeformAttnFusedFunction, ValueToBF16Function,
+                                             bf16_value_mode, fused_supported)
+
+
+def _current_bf16_mode() -> bool:
+    """the process-wide bf16 switch as it stands (modules without value_dtype leave it alone)"""
+    from ..functions.ms_deform_attn_func import get_bf16_value_mode
+    return get_bf16_value_mode()
 
 
 def _power_of_two(n) -> bool:
@@ -33,16 +40,26 @@ def _power_of_two(n) -> bool:
 
 class MSDeformAttn(nn.Module):
     def __init__(self, d_model: int = 256, n_levels: int = 4, n_heads: int = 8, n_points: int = 4,
-                 fuse_prologue: bool | None = None):
-        """``fuse_prologue`` (not in the reference; default off, or env MSDA_B200_FUSE_PROLOGUE=1): let the
-        kernels compute softmax(attention_weights) and reference + offsets / (W, H) themselves
-        instead of materialising sampling_locations / attention_weights.
-        Same parameters, same results to rounding; falls back to the unfused kernels when the fused
-        ones do not serve the operands (channels/head != 32, box references, non-fp32)."""
+                 fuse_prologue: bool | None = None, value_dtype: torch.dtype | None = None):
+        """Two switches that are not in the reference (same parameters, same checkpoints either way):
+
+        ``fuse_prologue`` (default ON; ``False`` or env MSDA_B200_FUSE_PROLOGUE=0 turns it off): the kernels compute
+        softmax(attention_weights) and reference + offsets / (W, H) themselves instead of materialising
+        sampling_locations / attention_weights (locations bit-identical to torch's, results
+        equal to rounding).  Applies to fp32, 32 channels per head, 2- or 42-dim reference points; everything
+        else (box references, other head sizes, half / double modules) takes the unfused kernels as before.
+
+        ``value_dtype=torch.bfloat16`` (default None = the reference's fp32 value): the value projection's output is
+        written ONCE as bf16 with the padding mask applied in the same pass and the bf16-value kernels gather from
+        it (half the gather bytes); grad_value is accumulated in fp32 and rounded once.
+        Output and the other gradients stay fp32; tolerance of this mode: 1e-2 (BASELINE.json north_star)."""
         super().__init__()
         if fuse_prologue is None:
-            fuse_prologue = os.environ.get("MSDA_B200_FUSE_PROLOGUE", "0") not in ("", "0", "false", "False")
+            fuse_prologue = os.environ.get("MSDA_B200_FUSE_PROLOGUE", "1") not in ("", "0", "false", "False")
         self.fuse_prologue = bool(fuse_prologue)
+        if value_dtype not in (None, torch.float32, torch.bfloat16):
+            raise ValueError("value_dtype must be None, torch.float32 or torch.bfloat16")
+        self.value_dtype = None if value_dtype == torch.float32 else value_dtype
         if d_model % n_heads != 0:
             raise ValueError(f"d_model must be divisible by n_heads, but got {d_model} and {n_heads}")
         if not _power_of_two(d_model // n_heads):
@@ -109,14 +126,19 @@ class MSDeformAttn(nn.Module):
         assert (input_spatial_shapes[:, 0] * input_spatial_shapes[:, 1]).sum() == len_in
 
         value = self.value_proj(input_flatten)
-        if input_padding_mask is not None:
+        bf16_value = (self.value_dtype == torch.bfloat16 and value.is_cuda and value.dtype == torch.float32
+                      and self.d_model // self.n_heads == 32 and self.n_levels <= 8
+                      and self.n_levels * self.n_points <= 32)
+        if bf16_value:
+            value = ValueToBF16Function.apply(value, input_padding_mask)      # mask + cast in one pass
+        elif input_padding_mask is not None:
             value = value.masked_fill(input_padding_mask[..., None], float(0))
         value = value.view(n, len_in, self.n_heads, self.d_model // self.n_heads)
         offsets = self.sampling_offsets(query).view(
             n, len_q, self.n_heads, self.n_levels, self.n_points, 2)
         weights = self.attention_weights(query).view(
             n, len_q, self.n_heads, self.n_levels * self.n_points)
-        if self.fuse_prologue and reference_points.shape[-1] in (2, 42):
+        if self.fuse_prologue and not bf16_value and reference_points.shape[-1] in (2, 42):
             centre = reference_points
             if reference_points.shape[-1] == 42:     # keypoint centre (ms_deform_attn.py:123-124), [N, Lq, L, 2]
                 centre = torch.stack([reference_points[..., 0::2].mean(-1), reference_points[..., 1::2].mean(-1)], -1)
@@ -135,6 +157,7 @@ class MSDeformAttn(nn.Module):
         else:
             if locations.dtype != weights.dtype:
                 locations = locations.to(weights.dtype)
-            out = MSDeformAttnFunction.apply(value, input_spatial_shapes, input_level_start_index,
-                                             locations.contiguous(), weights, self.im2col_step)
+            with bf16_value_mode(bf16_value or _current_bf16_mode()):
+                out = MSDeformAttnFunction.apply(value, input_spatial_shapes, input_level_start_index,
+                                                 locations.contiguous(), weights, self.im2col_step)
         return self.output_proj(out)
