@@ -1203,3 +1203,24 @@ def test_fused_prologue_through_the_tile_backward(case):
     close(res["grad_logits"], ref["grad_logits"], GRAD_RTOL)
     close(res["grad_ref"], ref["grad_ref"], GRAD_RTOL)
     assert np.array_equal(res2["grad_off"], res["grad_off"]) and res2["grad_ref"] is None
+
+
+@pytest.mark.parametrize("model", ["c3", "c4"])
+def test_layer_stack_graph_replay_against_the_oracle(model):
+    """the 6 encoder + 6 decoder operator calls of one model step (forward in order, backward in
+    reverse) captured as ONE CUDA graph; the replayed step's outputs and gradients of every layer are scored against
+    the ORACLE (tools/layer_stack.py), and a replay goes through no host launch path."""
+    sys_path = os.path.join(os.path.dirname(os.path.dirname(__file__)), "tools")
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("layer_stack", os.path.join(sys_path, "layer_stack.py"))
+    ls = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ls)
+    layers = ls.build_stack(model)
+    graph = ls.capture(layers)
+    ls.poison(layers)
+    n0 = cabi.launch_count()
+    graph.replay()
+    torch.cuda.synchronize()
+    assert cabi.launch_count() == n0
+    worst = ls.check_against_oracle(layers, frames=1, fwd_rtol=FWD_RTOL, grad_rtol=GRAD_RTOL)
+    assert worst["out"] <= FWD_RTOL and worst["grad_value"] <= GRAD_RTOL

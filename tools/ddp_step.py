@@ -4,7 +4,7 @@
 clip -- and that NCCL appears only in DDP's gradient all-reduce of the layer's parameters.
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 \
-        tools/ddp_step.py [--steps 20] [--workload c3_arctic_encoder] [--fuse]
+        tools/ddp_step.py [--steps 20] [--workload c3_arctic_encoder] [--no-fuse]
 
 Prints (rank 0) one JSON line: ms per step with DDP, ms per step of the same layer without DDP (no all-reduce),
 and the aggregate queries*heads/s of the operator inside the step.
@@ -26,7 +26,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--steps", type=int, default=20)
 ap.add_argument("--warmup", type=int, default=5)
 ap.add_argument("--workload", default="c3_arctic_encoder")
-ap.add_argument("--fuse", action="store_true")
+ap.add_argument("--no-fuse", action="store_true", help="materialise locations / weights with torch ops (the reference module)")
 a = ap.parse_args()
 
 world, rank, local = sharding.env_world()
@@ -34,7 +34,7 @@ torch.cuda.set_device(local)
 d = sharding.init_process_group("nccl", torch.device("cuda", local))
 wl = WORKLOADS[a.workload]
 torch.manual_seed(0)                                         # same parameters on every rank
-layer = MSDeformAttn(wl.M * wl.D, wl.L, wl.M, wl.P, fuse_prologue=a.fuse).cuda()
+layer = MSDeformAttn(wl.M * wl.D, wl.L, wl.M, wl.P, fuse_prologue=not a.no_fuse).cuda()
 with torch.no_grad():
     layer.sampling_offsets.weight.normal_(0, 0.01)
 ddp = torch.nn.parallel.DistributedDataParallel(layer, device_ids=[local]) if d is not None else layer
@@ -66,8 +66,9 @@ ms_local = run(layer, a.steps)
 ms_ddp, ms_local = sharding.max_over_ranks([ms_ddp, ms_local], d, "cuda")
 if rank == 0:
     n_param = sum(p.numel() for p in layer.parameters())
-    print(json.dumps({"workload": a.workload, "n_gpus": world, "fused_prologue": a.fuse,
+    print(json.dumps({"workload": a.workload, "n_gpus": world, "fused_prologue": not a.no_fuse,
                       "ms_per_step_ddp": ms_ddp, "ms_per_step_no_allreduce": ms_local,
+                      "allreduce_share_of_step": max(0.0, (ms_ddp - ms_local) / ms_ddp) if world > 1 else 0.0,
                       "allreduce_bytes_per_step": 4 * n_param,
                       "layer_items_per_s": sharding.aggregate_throughput(wl.items, world, ms_ddp * 1e-3),
                       "collectives_inside_the_operator": 0}))
