@@ -350,6 +350,35 @@ def main():
                "note": "host<->device copies dominate (PCIe); with N GPUs on one host the per-GPU value falls as the "
                        "ranks share the host's pinned-memory / PCIe root bandwidth -- not NCCL, not a kernel"}
         plan.close()
+        # the same call with bf16 storage for the two value-shaped tensors (value up, grad_value down): informational,
+        # the contract's e2e above is the fp32 reference-facing call
+        try:
+            v16 = np.ascontiguousarray(sets[0]["value"].to(torch.bfloat16).view(torch.int16).cpu().numpy().view(np.uint16))
+            gv16 = np.empty(v16.shape, np.uint16)
+            cabi.host_register(v16)
+            cabi.host_register(gv16)
+            plan16 = cabi.HostPlan(*wl.dims(), device=local_rank, value_bf16=True)
+            h2d16, d2h16 = plan16.traffic()
+
+            def e2e16_step():
+                plan16.forward_backward(v16, x["shapes"], x["lsi"], host["loc"], host["aw"], host["grad_out"],
+                                        outs["out"], gv16, outs["gl"], outs["ga"])
+            for _ in range(3):
+                e2e16_step()
+            barrier()
+            w0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                e2e16_step()
+            torch.cuda.synchronize()
+            e16 = sharding.max_over_ranks([(time.perf_counter() - w0) / e2e_steps], dist, "cuda")[0]
+            e2e["bf16_value_storage"] = {"value": sharding.aggregate_throughput(wl.items, n_gpus, e16), "ms_per_step": e16 * 1e3,
+                                         "h2d_bytes_per_step": h2d16, "d2h_bytes_per_step": d2h16,
+                                         "api": "msda_host_fwd_bwd_bf16 (value / grad_value travel as bf16; 1e-2 tolerance mode)"}
+            plan16.close()
+            cabi.host_unregister(v16)
+            cabi.host_unregister(gv16)
+        except Exception as exc:      # noqa: BLE001
+            e2e["bf16_value_storage"] = {"error": repr(exc)}
         for a in list(host.values()) + list(outs.values()):
             cabi.host_unregister(a)
 

@@ -1224,3 +1224,31 @@ def test_layer_stack_graph_replay_against_the_oracle(model):
     assert cabi.launch_count() == n0
     worst = ls.check_against_oracle(layers, frames=1, fwd_rtol=FWD_RTOL, grad_rtol=GRAD_RTOL)
     assert worst["out"] <= FWD_RTOL and worst["grad_value"] <= GRAD_RTOL
+
+
+def test_host_plan_bf16_storage_round_trip():
+    """msda_host_fwd_bwd_bf16: value up / grad_value down as bf16 (fp32 accumulation on the device, one rounding),
+    everything else fp32, against the oracle run on the bf16-rounded value."""
+    wl = Workload("h16", 2, ((20, 27), (10, 14), (5, 7), (3, 4)), 333, loc_dist="twostage")
+    x = np_inputs(wl, 33)
+    v16 = torch.from_numpy(x["value"]).to(torch.bfloat16)
+    v_bits = v16.view(torch.int16).numpy().view(np.uint16).copy()
+    v_round = v16.float().numpy()
+    plan = cabi.HostPlan(*wl.dims(), value_bf16=True)
+    out = np.full((wl.N, wl.Lq, wl.M * wl.D), np.nan, np.float32)
+    gv = np.zeros(x["value"].shape, np.uint16)
+    gl = np.full(x["loc"].shape, np.nan, np.float32)
+    ga = np.full(x["aw"].shape, np.nan, np.float32)
+    for _ in range(2):                                   # a plan is reusable
+        plan.forward_backward(v_bits, x["shapes"], x["lsi"], x["loc"], x["aw"], x["grad_out"], out, gv, gl, ga)
+    h2d, d2h = plan.traffic()
+    assert h2d < 4 * (x["value"].size + x["loc"].size + x["aw"].size + x["grad_out"].size)
+    with pytest.raises(ValueError):
+        plan.forward_backward(x["value"], x["shapes"], x["lsi"], x["loc"], x["aw"], x["grad_out"], out, gv, gl, ga)
+    plan.close()
+    ref = oracle(v_round, x["shapes"], x["lsi"], x["loc"], x["aw"], x["grad_out"])
+    close(out, ref["out"], FWD_RTOL)
+    close(gl, ref["grad_loc"], GRAD_RTOL)
+    close(ga, ref["grad_aw"], GRAD_RTOL)
+    gv_f = torch.from_numpy(gv.view(np.int16)).view(torch.bfloat16).float().numpy()
+    close(gv_f, ref["grad_value"], BF16_RTOL)

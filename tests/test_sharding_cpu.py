@@ -104,4 +104,6 @@ def test_reference_arm_under_two_ranks_only_rank0_prints():
     assert r.returncode == 0, r.stderr[-2000:]
     line = json.loads(r.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["n_gpus"] == 2 and line["value"] > 0
-    assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
+    # "reference" when __graft_entry__.build() staged the unmodified reference function (oracle/_ref/), else the port
+    assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["e2e"]["h2d_bytes_per_step"] == 0
+    assert line["steps"] == 1 and line["warmup"] == 1

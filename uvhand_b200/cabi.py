@@ -21,9 +21,10 @@ SYMBOLS = (
     "msda_fwd_f32", "msda_fwd_f64", "msda_fwd_bf16",
     "msda_bwd_f32", "msda_bwd_f64", "msda_bwd_bf16",
     "msda_fused_fwd_f32", "msda_fused_bwd_f32",
+    "msda_value_pack_bf16", "msda_value_unpack_grad_bf16",
     "msda_sample_index_f32",
-    "msda_host_plan_create", "msda_host_plan_destroy", "msda_host_plan_traffic",
-    "msda_host_register", "msda_host_unregister", "msda_host_fwd_f32", "msda_host_fwd_bwd_f32",
+    "msda_host_plan_create", "msda_host_plan_create_bf16", "msda_host_plan_destroy", "msda_host_plan_traffic",
+    "msda_host_register", "msda_host_unregister", "msda_host_fwd_f32", "msda_host_fwd_bwd_f32", "msda_host_fwd_bwd_bf16",
     "msda_b200_set_option", "msda_b200_get_option", "msda_b200_launch_count", "msda_b200_last_path",
 )
 
@@ -59,7 +60,11 @@ def lib() -> ctypes.CDLL:
         L.msda_fused_fwd_f32.argtypes = [c_void_p] * 6 + seven + [c_void_p, c_void_p]
         L.msda_fused_bwd_f32.argtypes = [c_void_p] * 7 + seven + [c_void_p] * 5
         L.msda_sample_index_f32.argtypes = [c_void_p, c_void_p] + [c_int] * 5 + [c_void_p] * 4
+        L.msda_value_pack_bf16.argtypes = [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p]
+        L.msda_value_unpack_grad_bf16.argtypes = [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p]
         L.msda_host_plan_create.argtypes = [ctypes.POINTER(c_void_p), c_int] + seven
+        L.msda_host_plan_create_bf16.argtypes = [ctypes.POINTER(c_void_p), c_int] + seven
+        L.msda_host_fwd_bwd_bf16.argtypes = [c_void_p] * 11
         L.msda_host_plan_destroy.argtypes = [c_void_p]
         L.msda_host_plan_destroy.restype = None
         L.msda_host_plan_traffic.argtypes = [c_void_p, ctypes.POINTER(c_int64), ctypes.POINTER(c_int64)]
@@ -141,10 +146,13 @@ def sample_index(shapes_ptr, loc_ptr, N, Lq, M, L, P, h_ptr, w_ptr, mask_ptr, st
 class HostPlan:
     """Owns device buffers + stream for one problem size; host (numpy) arrays in and out."""
 
-    def __init__(self, N, S, M, D, L, Lq, P, device: int = 0):
+    def __init__(self, N, S, M, D, L, Lq, P, device: int = 0, value_bf16: bool = False):
+        """value_bf16: `value` goes up and `grad_value` comes down as bf16 bit patterns (numpy uint16 arrays)."""
         self.dims = (N, S, M, D, L, Lq, P)
+        self.value_bf16 = bool(value_bf16)
         self._h = c_void_p()
-        check(lib().msda_host_plan_create(ctypes.byref(self._h), device, *self.dims), "msda_host_plan_create")
+        create = lib().msda_host_plan_create_bf16 if self.value_bf16 else lib().msda_host_plan_create
+        check(create(ctypes.byref(self._h), device, *self.dims), "msda_host_plan_create")
 
     def close(self):
         if self._h:
@@ -179,6 +187,8 @@ class HostPlan:
         sizes = self._sizes()
         for name, a in arrays.items():
             want = np.int64 if name in ("shapes", "lsi") else np.float32
+            if getattr(self, "value_bf16", False) and name in ("value", "gv"):
+                want = np.uint16
             if not isinstance(a, np.ndarray) or a.dtype != want:
                 raise ValueError(f"HostPlan: `{name}` must be a numpy array of {np.dtype(want).name}")
             if not a.flags["C_CONTIGUOUS"]:
@@ -196,7 +206,8 @@ class HostPlan:
     def forward_backward(self, value, shapes, lsi, loc, aw, grad_out, out, gv, gl, ga):
         self._validate(value=value, shapes=shapes, lsi=lsi, loc=loc, aw=aw, grad_out=grad_out, out=out, gv=gv, gl=gl,
                        ga=ga)
-        check(lib().msda_host_fwd_bwd_f32(self._h, self._p(value), self._p(shapes), self._p(lsi), self._p(loc),
+        fn = lib().msda_host_fwd_bwd_bf16 if self.value_bf16 else lib().msda_host_fwd_bwd_f32
+        check(fn(self._h, self._p(value), self._p(shapes), self._p(lsi), self._p(loc),
                                           self._p(aw), self._p(grad_out), self._p(out), self._p(gv),
                                           self._p(gl), self._p(ga)), "msda_host_fwd_bwd_f32")
 

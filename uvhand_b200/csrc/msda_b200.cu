@@ -501,6 +501,17 @@ int msda_bwd_f64(const double* go, const double* value, const int64_t* shapes, c
                          (cudaStream_t)stream);
 }
 
+// fp32 scratch -> bf16 grad_value (one rounding), `n4` groups of four elements
+static int round_scratch_to_bf16(const float* scratch, uint16_t* gv, long long n4, cudaStream_t st) {
+  if (n4 <= 0) return MSDA_OK;
+  long long blocks = (n4 + 255) / 256;
+  const long long cap = (long long)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  begin_call();
+  f32_to_bf16_kernel<<<(int)blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(scratch), reinterpret_cast<uint2*>(gv), n4);
+  return finish_launch(1);
+}
+
 int msda_bwd_bf16(const float* go, const uint16_t* value, const int64_t* shapes, const int64_t* lsi,
                   const float* loc, const float* aw, int N, int S, int M, int D, int L, int Lq, int P,
                   uint16_t* gv, float* gl, float* ga, float* gv_scratch, void* stream) {
@@ -530,13 +541,8 @@ int msda_bwd_bf16(const float* go, const uint16_t* value, const int64_t* shapes,
       rc = launch_bwd_d32<__nv_bfloat16, float>(p, st);
     }
     if (rc) return rc;
-    const long long n4 = (long long)N * S * M * 8;
-    long long blocks = (n4 + 255) / 256;
-    const long long cap = (long long)sm_count() * 16;
-    if (blocks > cap) blocks = cap;
-    f32_to_bf16_kernel<<<(int)blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(gv_scratch),
-                                                   reinterpret_cast<uint2*>(gv), n4);
-    return finish_launch(1);
+    if (gv == reinterpret_cast<uint16_t*>(gv_scratch)) return MSDA_OK;   // (host pipeline: rounding is done per sample later)
+    return round_scratch_to_bf16(gv_scratch, gv, (long long)N * S * M * 8, st);
   }
   p.grad_value = gv;
   if (use_tiles(p)) {
@@ -658,6 +664,9 @@ struct msda_host_plan {
   int N, S, M, D, L, Lq, P;
   size_t n_value, n_loc, n_aw, n_out;
   float *d_value, *d_loc, *d_aw, *d_go, *d_out, *d_gv, *d_gl, *d_ga;
+  int value_bf16;               // value and grad_value travel as bf16 (d_value holds bf16, d_gv is the fp32 accumulation
+  uint16_t* d_gv16;             // buffer, d_gv16 the rounded grad_value that is downloaded)
+  cudaEvent_t* ev_gv;           // [N] bf16 mode: grad_value[b] rounded
   int64_t *d_shapes, *d_lsi;
   // Three streams so that upload, kernels and download overlap (PCIe is full duplex and the copy
   // engines run beside the SMs): a call is cut into per-sample query chunks that flow through them.
@@ -678,8 +687,22 @@ struct msda_host_plan {
     if (e__ != cudaSuccess) return (int)e__;    \
   } while (0)
 
+static int plan_create(msda_host_plan** out_plan, int device, int N, int S, int M, int D, int L, int Lq, int P,
+                       int value_bf16);
+
 int msda_host_plan_create(msda_host_plan** out_plan, int device, int N, int S, int M, int D, int L,
                           int Lq, int P) {
+  return plan_create(out_plan, device, N, S, M, D, L, Lq, P, 0);
+}
+
+int msda_host_plan_create_bf16(msda_host_plan** out_plan, int device, int N, int S, int M, int D, int L,
+                               int Lq, int P) {
+  if (!d32_eligible(S > 0 ? S : 1, M > 0 ? M : 1, D, L > 0 ? L : 1, P > 0 ? P : 1)) return MSDA_ERR_UNSUPPORTED;
+  return plan_create(out_plan, device, N, S, M, D, L, Lq, P, 1);
+}
+
+static int plan_create(msda_host_plan** out_plan, int device, int N, int S, int M, int D, int L, int Lq, int P,
+                       int value_bf16) {
   if (!out_plan) return MSDA_ERR_NULL_POINTER;
   *out_plan = nullptr;
   int rc = check_dims(N, S, M, D, L, Lq, P);
@@ -695,6 +718,7 @@ int msda_host_plan_create(msda_host_plan** out_plan, int device, int N, int S, i
   if (!pl) return (int)cudaErrorMemoryAllocation;
   memset(pl, 0, sizeof(*pl));
   pl->device = device;
+  pl->value_bf16 = value_bf16;
   pl->N = N; pl->S = S; pl->M = M; pl->D = D; pl->L = L; pl->Lq = Lq; pl->P = P;
   pl->n_value = (size_t)N * S * M * D;
   pl->n_aw = (size_t)N * Lq * M * L * P;
@@ -730,12 +754,14 @@ int msda_host_plan_create(msda_host_plan** out_plan, int device, int N, int S, i
   pl->ev_in = new (std::nothrow) cudaEvent_t[n_ev]();
   pl->ev_run = new (std::nothrow) cudaEvent_t[n_ev]();
   pl->ev_value = new (std::nothrow) cudaEvent_t[N > 0 ? N : 1]();
-  if (!pl->ev_in || !pl->ev_run || !pl->ev_value) e = cudaErrorMemoryAllocation;
+  pl->ev_gv = new (std::nothrow) cudaEvent_t[N > 0 ? N : 1]();
+  if (!pl->ev_in || !pl->ev_run || !pl->ev_value || !pl->ev_gv) e = cudaErrorMemoryAllocation;
   for (int i = 0; i < n_ev && e == cudaSuccess; ++i) {
     e = cudaEventCreateWithFlags(&pl->ev_in[i], ev_flags);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&pl->ev_run[i], ev_flags);
   }
   for (int i = 0; i < N && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&pl->ev_value[i], ev_flags);
+  for (int i = 0; i < N && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&pl->ev_gv[i], ev_flags);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&pl->ev_tables, ev_flags);
   auto alloc = [&](float** p, size_t n) {
     if (e == cudaSuccess) e = cudaMalloc((void**)p, sizeof(float) * (n ? n : 1));
@@ -746,6 +772,7 @@ int msda_host_plan_create(msda_host_plan** out_plan, int device, int N, int S, i
   alloc(&pl->d_go, pl->n_out);
   alloc(&pl->d_out, pl->n_out);
   alloc(&pl->d_gv, pl->n_value);
+  if (value_bf16 && e == cudaSuccess) e = cudaMalloc((void**)&pl->d_gv16, sizeof(uint16_t) * (pl->n_value ? pl->n_value : 1));
   alloc(&pl->d_gl, pl->n_loc);
   alloc(&pl->d_ga, pl->n_aw);
   if (e == cudaSuccess) e = cudaMalloc((void**)&pl->d_shapes, sizeof(int64_t) * 2 * (L ? L : 1));
@@ -763,14 +790,18 @@ void msda_host_plan_destroy(msda_host_plan* pl) {
   cudaSetDevice(pl->device);
   cudaFree(pl->d_value); cudaFree(pl->d_loc); cudaFree(pl->d_aw); cudaFree(pl->d_go);
   cudaFree(pl->d_out); cudaFree(pl->d_gv); cudaFree(pl->d_gl); cudaFree(pl->d_ga);
+  cudaFree(pl->d_gv16);
   cudaFree(pl->d_shapes); cudaFree(pl->d_lsi);
   const int n_ev = (pl->N > 0 ? pl->N : 1) * pl->n_chunks;
   for (int i = 0; i < n_ev; ++i) {
     if (pl->ev_in && pl->ev_in[i]) cudaEventDestroy(pl->ev_in[i]);
     if (pl->ev_run && pl->ev_run[i]) cudaEventDestroy(pl->ev_run[i]);
   }
-  for (int i = 0; i < pl->N; ++i)
+  for (int i = 0; i < pl->N; ++i) {
     if (pl->ev_value && pl->ev_value[i]) cudaEventDestroy(pl->ev_value[i]);
+    if (pl->ev_gv && pl->ev_gv[i]) cudaEventDestroy(pl->ev_gv[i]);
+  }
+  delete[] pl->ev_gv;
   if (pl->ev_out) {
     for (int i = 0; i < n_ev + pl->N; ++i)
       if (pl->ev_out[i]) cudaEventDestroy(pl->ev_out[i]);
@@ -786,9 +817,10 @@ void msda_host_plan_destroy(msda_host_plan* pl) {
 
 int msda_host_plan_traffic(const msda_host_plan* pl, int64_t* h2d, int64_t* d2h) {
   if (!pl) return MSDA_ERR_NULL_POINTER;
-  const int64_t in = (int64_t)sizeof(float) * (pl->n_value + pl->n_loc + pl->n_aw + pl->n_out) +
+  const int64_t vb = pl->value_bf16 ? 2 : 4;
+  const int64_t in = vb * (int64_t)pl->n_value + (int64_t)sizeof(float) * (pl->n_loc + pl->n_aw + pl->n_out) +
                      (int64_t)sizeof(int64_t) * 3 * pl->L;
-  const int64_t out = (int64_t)sizeof(float) * (pl->n_out + pl->n_value + pl->n_loc + pl->n_aw);
+  const int64_t out = vb * (int64_t)pl->n_value + (int64_t)sizeof(float) * (pl->n_out + pl->n_loc + pl->n_aw);
   if (h2d) *h2d = in;
   if (d2h) *d2h = out;
   return MSDA_OK;
@@ -821,9 +853,14 @@ static cudaError_t copy_batch(void** dsts, void** srcs, size_t* sizes, int n, cu
 //   s_out: per chunk: out (, grad_loc, grad_aw); after the last chunk of a sample: grad_value[b]
 // The kernels see each packet as a problem with batch 1 and q1-q0 queries (the operator has no
 // cross-query or cross-sample term), so nothing but pointer offsets is needed.
-static int host_pipeline(msda_host_plan* pl, const float* value, const int64_t* shapes, const int64_t* lsi,
-                         const float* loc, const float* aw, const float* go, float* out, float* gv,
+static int host_pipeline(msda_host_plan* pl, const void* value_any, const int64_t* shapes, const int64_t* lsi,
+                         const float* loc, const float* aw, const float* go, float* out, void* gv_any,
                          float* gl, float* ga) {
+  const bool b16 = pl->value_bf16 != 0;
+  const size_t vsz = b16 ? 2 : 4;
+  const char* value = static_cast<const char*>(value_any);
+  char* gv = static_cast<char*>(gv_any);
+  char* d_value = reinterpret_cast<char*>(pl->d_value);
   const bool bwd = go != nullptr;
   const int N = pl->N, S = pl->S, M = pl->M, D = pl->D, L = pl->L, Lq = pl->Lq, P = pl->P;
   if (N == 0) return MSDA_OK;
@@ -836,7 +873,7 @@ static int host_pipeline(msda_host_plan* pl, const float* value, const int64_t* 
   MSDA_CUDA_TRY(cudaStreamWaitEvent(pl->s_run, pl->ev_tables, 0));
   if (bwd && pl->n_value) MSDA_CUDA_TRY(cudaMemsetAsync(pl->d_gv, 0, sizeof(float) * pl->n_value, pl->s_run));
   for (int b = 0; b < N; ++b) {
-    if (v_per) MSDA_CUDA_TRY(cudaMemcpyAsync(pl->d_value + b * v_per, value + b * v_per, sizeof(float) * v_per, H2D, pl->s_in));
+    if (v_per) MSDA_CUDA_TRY(cudaMemcpyAsync(d_value + b * v_per * vsz, value + b * v_per * vsz, vsz * v_per, H2D, pl->s_in));
     MSDA_CUDA_TRY(cudaEventRecord(pl->ev_value[b], pl->s_in));
     MSDA_CUDA_TRY(cudaStreamWaitEvent(pl->s_run, pl->ev_value[b], 0));
     for (int c = 0; c < pl->n_chunks; ++c) {
@@ -864,13 +901,25 @@ static int host_pipeline(msda_host_plan* pl, const float* value, const int64_t* 
       MSDA_CUDA_TRY(cudaEventRecord(pl->ev_in[k], pl->s_in));
       MSDA_CUDA_TRY(cudaStreamWaitEvent(pl->s_run, pl->ev_in[k], 0));
       if (nq > 0) {
-        int rc = msda_fwd_f32(pl->d_value + b * v_per, pl->d_shapes, pl->d_lsi, pl->d_loc + qo * a_per_q * 2,
-                              pl->d_aw + qo * a_per_q, 1, S, M, D, L, nq, P, pl->d_out + qo * o_per_q, pl->s_run);
+        int rc;
+        if (b16)
+          rc = msda_fwd_bf16(reinterpret_cast<const uint16_t*>(d_value) + b * v_per, pl->d_shapes, pl->d_lsi,
+                             pl->d_loc + qo * a_per_q * 2, pl->d_aw + qo * a_per_q, 1, S, M, D, L, nq, P,
+                             pl->d_out + qo * o_per_q, pl->s_run);
+        else
+          rc = msda_fwd_f32(pl->d_value + b * v_per, pl->d_shapes, pl->d_lsi, pl->d_loc + qo * a_per_q * 2,
+                            pl->d_aw + qo * a_per_q, 1, S, M, D, L, nq, P, pl->d_out + qo * o_per_q, pl->s_run);
         if (rc) return rc;
         if (bwd) {
-          rc = msda_bwd_f32(pl->d_go + qo * o_per_q, pl->d_value + b * v_per, pl->d_shapes, pl->d_lsi,
-                            pl->d_loc + qo * a_per_q * 2, pl->d_aw + qo * a_per_q, 1, S, M, D, L, nq, P,
-                            pl->d_gv + b * v_per, pl->d_gl + qo * a_per_q * 2, pl->d_ga + qo * a_per_q, pl->s_run);
+          if (b16)   // fp32 accumulation into d_gv; rounded to bf16 once per sample below (gv == scratch: no rounding here)
+            rc = msda_bwd_bf16(pl->d_go + qo * o_per_q, reinterpret_cast<const uint16_t*>(d_value) + b * v_per, pl->d_shapes,
+                               pl->d_lsi, pl->d_loc + qo * a_per_q * 2, pl->d_aw + qo * a_per_q, 1, S, M, D, L, nq, P,
+                               reinterpret_cast<uint16_t*>(pl->d_gv + b * v_per), pl->d_gl + qo * a_per_q * 2,
+                               pl->d_ga + qo * a_per_q, pl->d_gv + b * v_per, pl->s_run);
+          else
+            rc = msda_bwd_f32(pl->d_go + qo * o_per_q, pl->d_value + b * v_per, pl->d_shapes, pl->d_lsi,
+                              pl->d_loc + qo * a_per_q * 2, pl->d_aw + qo * a_per_q, 1, S, M, D, L, nq, P,
+                              pl->d_gv + b * v_per, pl->d_gl + qo * a_per_q * 2, pl->d_ga + qo * a_per_q, pl->s_run);
           if (rc) return rc;
         }
       }
@@ -889,8 +938,17 @@ static int host_pipeline(msda_host_plan* pl, const float* value, const int64_t* 
       }
       if (pl->trace && pl->ev_out) cudaEventRecord(pl->ev_out[k], pl->s_out);
     }
-    if (bwd && v_per)
-      MSDA_CUDA_TRY(cudaMemcpyAsync(gv + b * v_per, pl->d_gv + b * v_per, sizeof(float) * v_per, D2H, pl->s_out));
+    if (bwd && v_per) {
+      if (b16) {
+        const int rc = round_scratch_to_bf16(pl->d_gv + b * v_per, pl->d_gv16 + b * v_per, (long long)(v_per / 4), pl->s_run);
+        if (rc) return rc;
+        MSDA_CUDA_TRY(cudaEventRecord(pl->ev_gv[b], pl->s_run));
+        MSDA_CUDA_TRY(cudaStreamWaitEvent(pl->s_out, pl->ev_gv[b], 0));
+        MSDA_CUDA_TRY(cudaMemcpyAsync(gv + b * v_per * 2, pl->d_gv16 + b * v_per, 2 * v_per, D2H, pl->s_out));
+      } else {
+        MSDA_CUDA_TRY(cudaMemcpyAsync(gv + b * v_per * 4, pl->d_gv + b * v_per, sizeof(float) * v_per, D2H, pl->s_out));
+      }
+    }
     if (pl->trace && pl->ev_out) cudaEventRecord(pl->ev_out[N * pl->n_chunks + b], pl->s_out);
   }
   MSDA_CUDA_TRY(cudaStreamSynchronize(pl->s_out));
@@ -925,6 +983,7 @@ static int host_finish(msda_host_plan* pl, int rc) {
 int msda_host_fwd_f32(msda_host_plan* pl, const float* value, const int64_t* shapes, const int64_t* lsi,
                       const float* loc, const float* aw, float* out) {
   if (!pl || !value || !shapes || !lsi || !loc || !aw || !out) return MSDA_ERR_NULL_POINTER;
+  if (pl->value_bf16) return MSDA_ERR_UNSUPPORTED;
   MSDA_CUDA_TRY(cudaSetDevice(pl->device));
   return host_finish(pl, host_pipeline(pl, value, shapes, lsi, loc, aw, nullptr, out, nullptr, nullptr, nullptr));
 }
@@ -934,6 +993,17 @@ int msda_host_fwd_bwd_f32(msda_host_plan* pl, const float* value, const int64_t*
                           float* out, float* gv, float* gl, float* ga) {
   if (!pl || !value || !shapes || !lsi || !loc || !aw || !go || !out || !gv || !gl || !ga)
     return MSDA_ERR_NULL_POINTER;
+  if (pl->value_bf16) return MSDA_ERR_UNSUPPORTED;
+  MSDA_CUDA_TRY(cudaSetDevice(pl->device));
+  return host_finish(pl, host_pipeline(pl, value, shapes, lsi, loc, aw, go, out, gv, gl, ga));
+}
+
+int msda_host_fwd_bwd_bf16(msda_host_plan* pl, const uint16_t* value, const int64_t* shapes,
+                           const int64_t* lsi, const float* loc, const float* aw, const float* go,
+                           float* out, uint16_t* gv, float* gl, float* ga) {
+  if (!pl || !value || !shapes || !lsi || !loc || !aw || !go || !out || !gv || !gl || !ga)
+    return MSDA_ERR_NULL_POINTER;
+  if (!pl->value_bf16) return MSDA_ERR_UNSUPPORTED;
   MSDA_CUDA_TRY(cudaSetDevice(pl->device));
   return host_finish(pl, host_pipeline(pl, value, shapes, lsi, loc, aw, go, out, gv, gl, ga));
 }
