@@ -242,7 +242,7 @@ int launch_bwd_tiles(D32Params& p, cudaStream_t st) {
   begin_call();
   const int grid_mode = p.Lq == p.S ? 1 : 0;
   auto kernel = bwd_d32_tile_kernel<VT, GT, kFuse>;
-#if MSDA_TILE_EXPERIMENT == 4      // timing experiment: one unit per SM (how much do two resident units overlap?)
+#if MSDA_TILE_EXPERIMENT == 4 || defined(MSDA_TILE_ONE_PER_SM)   // timing experiment: one unit per SM
   const size_t smem = tile_smem_bytes() + 100 * 1024;
 #else
   const size_t smem = tile_smem_bytes();
