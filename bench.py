@@ -57,6 +57,7 @@ def parse_args():
     ap.add_argument("--extended", action="store_true", help="also time the other workloads / kernels")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--main-only", action="store_true", help="skip the other-workloads / prologue blocks (launch lists)")
     return ap.parse_args()
 
 
@@ -384,7 +385,7 @@ def main():
 
     # ---- extras: other kernels / workloads (rank 0, not part of the contract keys) ------------
     extras, other, prologue = {}, {}, {}
-    if rank == 0 and n_gpus == 1:
+    if rank == 0 and n_gpus == 1 and not args.main_only:
         del sets, bufs
         torch.cuda.empty_cache()
         other = other_workloads(torch, cabi)

@@ -195,7 +195,7 @@ int msda_host_fwd_bwd_bf16(msda_host_plan *plan, const uint16_t *value, const in
  * decoder queries use the one-item-per-warp kernels, large ones four items per warp), 1 = never
  * split, 2 = always split; "bwd_tiles": the backward that combines grad_value rows on chip before they leave
  * the SM (num_levels = num_point = 4): 0 = chosen by shape (encoder self-attention num_query == spatial_size, or a
- * pyramid of at most 1600 tokens), 1 = never, 2 = whenever the shape is eligible; "fwd_wide": the forward with 4 lanes
+ * pyramid of at most 1500 tokens), 1 = never, 2 = whenever the shape is eligible; "fwd_wide": the forward with 4 lanes
  * per (query, head) and 8 channels per lane (num_levels = num_point = 4): 0 = for bf16 values, 1 = never, 2 = also for
  * fp32 values.  None of these changes results
  * beyond summation order.  Options are process-global (every thread and stream sees them); they exist for tests and

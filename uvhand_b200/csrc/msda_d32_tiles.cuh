@@ -32,8 +32,8 @@
 //
 // Windows: per level min(W + 1, 20) x min(H, 20) keys positioned at the mean sample position of the unit
 // (data-driven: correctness never depends on where the queries are), or the whole pyramid when its
-// H x (W + 1) keys fit the table (ARCTIC: 1098).  Row pairs outside the window become single-entry keys of their own
-// ("leftover" keys: same code path, no combining).  Query tiles: 8x8 pixel blocks of each level when
+// H x (W + 1) keys fit the table (ARCTIC: 1098).  Row pairs outside the window are served on their own after the window
+// keys (no combining, any number of them: their entries carry the pair's token).  Query tiles: 8x8 pixel blocks of each level when
 // Lq == S (encoder self-attention: query i is token i), else 64 consecutive queries.
 // The next unit's sampling locations / weights / grad_out rows are copied asynchronously (cp.async) while the
 // current unit is processed.
@@ -59,9 +59,9 @@ constexpr int kTileSamples = kTileQ * kTileLP;    // 1024: two per thread
 constexpr int kTileEntries = kTileSamples * 2;    // 2048 row-pair contributions at most (two per sample)
 constexpr int kTileDots = kTileSamples * 4;       // one dot product per bilinear corner
 constexpr int kWinDim = 20;                       // window edge per level when the pyramid is large
-constexpr int kRowCap = 1792;                     // window keys + leftover keys
-constexpr int kWholeMaxRows = 1600;               // host side: pyramids up to this many tokens are expected to be windowed whole
-constexpr int kWholeMaxKeys = kRowCap - 64;       // device side: ... when their H x (W + 1) keys fit the table
+constexpr int kRowCap = 1664;                     // window keys (4 levels x 20 x 20, or a whole small pyramid)
+constexpr int kWholeMaxRows = 1500;               // host side: pyramids up to this many tokens are expected to be windowed whole
+constexpr int kWholeMaxKeys = kRowCap;            // device side: ... when their H x (W + 1) keys fit the table
 constexpr int kSplit = 32;                        // longer entry lists are cut into virtual keys
 constexpr int kBins = kSplit + 1;
 constexpr int kRowListCap = kRowCap + kTileEntries / kSplit;
@@ -74,8 +74,9 @@ struct TileUnit {          // decoded once per unit by thread 0
 
 struct TileShared {
   float4 G[kTileQ * 8];                 // grad_out rows of the unit's queries (8 KB)
-  uint4 entries[kTileEntries];          // {coef left, coef right, sample * 2 + (0 top | 1 bottom), -}: window keys' lists from
-                                        // the front, leftovers from the back (32 KB)
+  uint4 entries[kTileEntries];          // window keys' lists from the front: {coef left, coef right, byte offset of the pair's two
+                                        // dots in dbuf, byte offset of the query's row in G}; row pairs outside the windows from
+                                        // the back: {coef left, coef right, G offset << 16 | dbuf offset, packed token} (32 KB)
   float dbuf[kTileDots];                // <G[q], value row> per (sample, corner) (16 KB)
   float4 rec[kTileSamples];             // {lh, lw, attention weight, (query + 1) << 5 | accepted << 4 | corner mask} (16 KB)
   int hw[kTileSamples];                 // h_low << 16 | (w_low & 0xffff) per sample (4 KB)
@@ -83,7 +84,7 @@ struct TileShared {
   float stage_aw[kTileSamples];         // this unit is processed (12 KB): their HBM latency never heads a unit
   int off[kRowCap + 8];                 // counts per key; then exclusive offsets
   int rowtok[kRowCap + 8];              // (token * M of the key's LEFT row) << 2 | right row exists << 1 | left row exists,
-                                        // of every touched window key ([0, R)) and leftover key ((R, ..))
+                                        // of every touched window key
   unsigned rowlist[kRowListCap];        // first entry << 18 | count << 12 | key, longest first
   int whist[kTileWarps][kBins + 1];     // per-warp histogram of list lengths -> per-warp scatter cursors
   int wsum[kTileWarps];
@@ -97,6 +98,20 @@ struct TileShared {
 static_assert(2 * (sizeof(TileShared) + 1024) <= 228 * 1024, "two units per SM");
 
 __device__ __forceinline__ float4 zero4() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+// shared-memory accesses by 32-bit shared address
+__device__ __forceinline__ float4 lds128(unsigned addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint4 lds128u(unsigned addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts32(unsigned addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
 __device__ __forceinline__ TileShared& tile_smem() {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   return *reinterpret_cast<TileShared*>(smem_raw);
@@ -174,27 +189,13 @@ __device__ __noinline__ void request_grad_rows(const D32Params& p, int slot, int
   else sh.G[t] = zero4();
 }
 
-// One corner contribution served by a single thread (the overflow path of the unit's key table).
-template <typename VT, typename GT>
-__device__ __noinline__ float lone_contribution(const typename Chunk<VT>::Vec* vr, typename Chunk<GT>::Vec* gr,
-                                                const float4* g_row, float coef) {
-  float d = 0.f;
-  for (int ch = 0; ch < 8; ++ch) {
-    const float4 g = g_row[ch];
-    d += dot4(g, Chunk<VT>::load(vr + ch));
-    Chunk<GT>::red_add(gr + ch, scale4(coef, g));
-  }
-  return d;
-}
-
-// A row pair outside the unit's window: becomes a single-entry key of its own, its entry goes to the back of the
-// entry array right away.  Returns false when the key table is full (the caller then serves the corners alone).
-__device__ __noinline__ bool leftover_pair(TileShared& sh, int R, int packed_tok, float coef_l, float coef_r, unsigned sc2) {
+// A row pair outside the unit's window: no combining, it is served on its own after the window keys.  Its entry goes to
+// the back of the entry array (window entries + leftovers <= 2048 = all pairs of the unit: they cannot meet) and carries
+// the pair's token itself, so any number of pairs may miss the windows (locations unrelated to the query grid).
+__device__ __forceinline__ void leftover_pair(TileShared& sh, int packed_tok, float coef_l, float coef_r, unsigned sc2) {
   const int k = atomicAdd(&sh.n_left, 1);
-  if (k >= kRowCap - R - 1) return false;
-  sh.rowtok[R + 1 + k] = packed_tok;
-  sh.entries[kTileEntries - 1 - k] = make_uint4(__float_as_uint(coef_l), __float_as_uint(coef_r), sc2, 0u);
-  return true;
+  sh.entries[kTileEntries - 1 - k] = make_uint4(__float_as_uint(coef_l), __float_as_uint(coef_r),
+                                                (((sc2 >> 5) * 128u) << 16) | (sc2 * 8u), (unsigned)packed_tok);
 }
 
 // ---- geometry: this thread's two samples (local query (t >> 4) + 32 i, level / point t & 15) -----------------------
@@ -257,15 +258,12 @@ __device__ __noinline__ void tile_geometry(const D32Params& p, int slot, int gri
 
 // ---- sort: count per key, scan, entries into their keys' lists, key list longest first ------------------------------
 // (contains barriers: called by every thread of the CTA)
-template <typename VT, typename GT>
-__device__ __noinline__ void tile_sort(const D32Params& p, int slot, int next_slot, int grid_mode) {
-  using Vec = typename Chunk<VT>::Vec;
-  using GVec = typename Chunk<GT>::Vec;
+__device__ __noinline__ void tile_sort(const D32Params& p, int next_slot, int grid_mode) {
   TileShared& sh = tile_smem();
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   const int l = (t & 15) >> 2;
   const int M = p.M;
-  const int R = sh.wbase[kTileL];             // window keys; leftover keys live at R + 1 + k
+  const int R = sh.wbase[kTileL];             // window keys
   unsigned slot_of[2][2];                     // per row pair (0 top, 1 bottom): key (12 bits) | rank << 12 | bit 31, or 0
   {
     const int Hl = sh.tab.H[l], Wl = sh.tab.W[l];
@@ -309,21 +307,7 @@ __device__ __noinline__ void tile_sort(const D32Params& p, int slot, int next_sl
             const float4 rc = sh.rec[t + kTileThreads * i];
             const float wy = (r ? rc.x : 1.f - rc.x) * rc.z;
             const float cl = (pair & 1u) ? wy * (1.f - rc.y) : 0.f, cr = (pair & 2u) ? wy * rc.y : 0.f;
-            const unsigned sc2 = (unsigned)((t + kTileThreads * i) * 2 + r);
-            if (!leftover_pair(sh, R, packed_tok, cl, cr, sc2)) {
-              // no room left in the unit's key table: this thread alone serves the two rows (slow; only when
-              // the windows miss almost everything, which the host-side kernel choice avoids)
-              const TileUnit un = sh.unit[slot];
-#pragma unroll 1
-              for (int c = 0; c < 2; ++c) {
-                if ((pair >> c) & 1u) {
-                  const long long ro = ((long long)un.b * p.S * M + (long long)(tok0 + r * Wl + c) * M + un.m) * 8;
-                  sh.dbuf[sc2 * 2 + c] = lone_contribution<VT, GT>(reinterpret_cast<const Vec*>(p.value) + ro,
-                                                                   reinterpret_cast<GVec*>(p.grad_value) + ro,
-                                                                   sh.G + (sc2 >> 5) * 8, c ? cr : cl);
-                }
-              }
-            }
+            leftover_pair(sh, packed_tok, cl, cr, (unsigned)((t + kTileThreads * i) * 2 + r));
           }
         }
       }
@@ -414,7 +398,8 @@ __device__ __noinline__ void tile_sort(const D32Params& p, int slot, int next_sl
           const unsigned pair = (msk >> (2 * r)) & 3u;
           const int pos = sh.off[slot_of[i][r] & 0xfff] + (int)((slot_of[i][r] >> 12) & 0x7ffff);
           const float cl = (pair & 1u) ? ay[r] * hw : 0.f, cr = (pair & 2u) ? ay[r] * rc.y : 0.f;
-          sh.entries[pos] = make_uint4(__float_as_uint(cl), __float_as_uint(cr), (unsigned)((t + kTileThreads * i) * 2 + r), 0u);
+          const unsigned sc2 = (unsigned)((t + kTileThreads * i) * 2 + r);
+          sh.entries[pos] = make_uint4(__float_as_uint(cl), __float_as_uint(cr), sc2 * 8u, (sc2 >> 5) * 128u);
         }
       }
     }
@@ -440,10 +425,6 @@ __device__ __noinline__ void tile_sort(const D32Params& p, int slot, int next_sl
       }
     }
   }
-  const int n_left = min(sh.n_left, kRowCap - R - 1);
-  const int n_vrows = sh.n_vrows;
-  for (int k = t; k < n_left; k += kTileThreads)
-    sh.rowlist[n_vrows + k] = ((unsigned)(kTileEntries - 1 - k) << 18) | (1u << 12) | (unsigned)(R + 1 + k);
 }
 
 // ---- keys: key-centric accumulation -------------------------------------------------------------------------------
@@ -460,13 +441,15 @@ __device__ __noinline__ void tile_keys(const void* value, void* grad_value, unsi
   using GVec = typename Gc::Vec;
   TileShared& sh = tile_smem();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int n_rows = sh.n_vrows + min(sh.n_left, kRowCap - sh.wbase[kTileL] - 1);
+  const int n_rows = sh.n_vrows;
   const int g = lane >> 2, h = lane & 3;
   const int first = 4 * (g & 1) + h;
   const Vec* vb = reinterpret_cast<const Vec*>(value);
   GVec* gvb = reinterpret_cast<GVec*>(grad_value);
-  const float4* GA = sh.G + first;
-  const float4* GB = sh.G + (first ^ 4);
+  const unsigned ga_base = (unsigned)__cvta_generic_to_shared(sh.G + first);
+  const unsigned gb_base = (unsigned)__cvta_generic_to_shared(sh.G + (first ^ 4));
+  const unsigned ent_base = (unsigned)__cvta_generic_to_shared(sh.entries);
+  const unsigned dot_base = (unsigned)__cvta_generic_to_shared(sh.dbuf) + (unsigned)(h >> 1) * 4u;
   // Passes (8 keys each): the first three quarters go to the warps in serpentine order (lists are sorted by length,
   // so straight round robin would hand warp 0 the longest pass of every round), the rest is handed out by a
   // shared counter so that the warps reach the barrier together.
@@ -489,7 +472,6 @@ __device__ __noinline__ void tile_keys(const void* value, void* grad_value, unsi
     const bool has = j < n_rows;
     const unsigned rl = has ? sh.rowlist[j] : 0u;
     const int c = (int)((rl >> 12) & 63u);
-    const uint4* ep = sh.entries + (rl >> 18);
     // lists are sorted by length: group 0 has the longest, group 7 the shortest of the pass
 #if MSDA_TILE_EXPERIMENT == 3      // timing experiment: no entry loop at all
     const int cmax = 0, cmin = 0;
@@ -505,9 +487,9 @@ __device__ __noinline__ void tile_keys(const void* value, void* grad_value, unsi
     float4 aLA = zero4(), aLB = zero4(), aRA = zero4(), aRB = zero4();
     // the two dot products of an entry are reduced together: lanes h = 0, 1 end up with the left row's, h = 2, 3
     // with the right row's; dbuf index = sample * 4 + (top | bottom) * 2 + (left | right)
+    // shared-memory addresses are carried as 32-bit offsets: one add per access, no generic-address arithmetic
     auto one = [&](const uint4 e, bool store) {
-      const unsigned qq = (e.z >> 5) << 3;
-      const float4 a0 = GA[qq], b0 = GB[qq];
+      const float4 a0 = lds128(ga_base + e.w), b0 = lds128(gb_base + e.w);
       const float cl = __uint_as_float(e.x), cr = __uint_as_float(e.y);
       fma4(aLA, cl, a0);
       fma4(aLB, cl, b0);
@@ -518,16 +500,17 @@ __device__ __noinline__ void tile_keys(const void* value, void* grad_value, unsi
       const float dr = dot4(a0, vRA) + dot4(b0, vRB);
       float r = ((h & 2) ? dr : dl) + __shfl_xor_sync(kFull, (h & 2) ? dl : dr, 2);
       r += __shfl_xor_sync(kFull, r, 1);
-      if (store && (h & 1) == 0) sh.dbuf[e.z * 2 + (h >> 1)] = r;
+      if (store && (h & 1) == 0) sts32(dot_base + e.z, r);
 #endif
     };
+    const unsigned ep = ent_base + (rl >> 18) * 16u;
     int i = 0;
 #pragma unroll 2
-    for (; i < cmin; ++i) one(ep[i], true);          // every group has at least cmin entries: no predicates
+    for (; i < cmin; ++i) one(lds128u(ep + i * 16), true);          // every group has at least cmin entries: no predicates
     for (; i < cmax; ++i) {
       const bool act = i < c;
       uint4 e = make_uint4(0u, 0u, 0u, 0u);
-      if (act) e = ep[i];
+      if (act) e = lds128u(ep + i * 16);
       one(e, act);
     }
     if (has_l) {
@@ -539,6 +522,38 @@ __device__ __noinline__ void tile_keys(const void* value, void* grad_value, unsi
       Gc::red_add(gvb + (ro_r + (first ^ 4)), aRB);
     }
   }
+  // ---- row pairs outside the windows: one pair per 4-lane group, nothing to combine (their entries carry the token)
+  {
+    const int n_left = sh.n_left;
+    for (int k0 = warp * kBatchRows; k0 < n_left; k0 += kTileWarps * kBatchRows) {
+      const int k = k0 + g;
+      const bool has = k < n_left;
+      uint4 e = make_uint4(0u, 0u, 0u, 0u);
+      if (has) e = lds128u(ent_base + (unsigned)(kTileEntries - 1 - k) * 16u);
+      const int packed_tok = (int)e.w;
+      const bool has_l = has && (packed_tok & 1), has_r = has && (packed_tok & 2);
+      const unsigned ro_l = head + (unsigned)((packed_tok >> 2) * 8), ro_r = ro_l + row_stride;
+      float4 vLA = zero4(), vLB = zero4(), vRA = zero4(), vRB = zero4();
+      if (has_l) { vLA = C::load(vb + (ro_l + first)); vLB = C::load(vb + (ro_l + (first ^ 4))); }
+      if (has_r) { vRA = C::load(vb + (ro_r + first)); vRB = C::load(vb + (ro_r + (first ^ 4))); }
+      const float4 a0 = lds128(ga_base + (e.z >> 16)), b0 = lds128(gb_base + (e.z >> 16));
+      const float cl = __uint_as_float(e.x), cr = __uint_as_float(e.y);
+      const float dl = dot4(a0, vLA) + dot4(b0, vLB);
+      const float dr = dot4(a0, vRA) + dot4(b0, vRB);
+      float r = ((h & 2) ? dr : dl) + __shfl_xor_sync(kFull, (h & 2) ? dl : dr, 2);
+      r += __shfl_xor_sync(kFull, r, 1);
+      if (has && (h & 1) == 0) sts32(dot_base + (e.z & 0xffffu), r);
+      if (has_l) {
+        Gc::red_add(gvb + (ro_l + first), scale4(cl, a0));
+        Gc::red_add(gvb + (ro_l + (first ^ 4)), scale4(cl, b0));
+      }
+      if (has_r) {
+        Gc::red_add(gvb + (ro_r + first), scale4(cr, a0));
+        Gc::red_add(gvb + (ro_r + (first ^ 4)), scale4(cr, b0));
+      }
+    }
+  }
+  __syncwarp();
   // nothing in this phase reads the counters: clear them for the next unit before the barrier that follows
   {
     const int t = threadIdx.x;
@@ -546,7 +561,6 @@ __device__ __noinline__ void tile_keys(const void* value, void* grad_value, unsi
     for (int i = t; i < Rz; i += kTileThreads) sh.off[i] = 0;
     for (int i = t; i < kTileWarps * (kBins + 1); i += kTileThreads) (&sh.whist[0][0])[i] = 0;
     if (t < kTileL * 3) (&sh.anchor_sum[0][0])[t] = 0;
-    if (t == 0) sh.n_left = 0;
   }
 }
 
@@ -557,7 +571,7 @@ __device__ __noinline__ void tile_epilogue(const D32Params& p, int slot) {
   TileShared& sh = tile_smem();
   const int t = threadIdx.x;
   const TileUnit un = sh.unit[slot];
-  if (t == 0) sh.next_pass = 0;
+  if (t == 0) { sh.next_pass = 0; sh.n_left = 0; }      // (read by the key phase: reset behind its barrier)
   const int l = (t & 15) >> 2;
   const float Wf = (float)sh.tab.W[l], Hf = (float)sh.tab.H[l];
   const unsigned qb = (unsigned)un.b * (unsigned)p.Lq;
@@ -674,7 +688,7 @@ bwd_d32_tile_kernel(const __grid_constant__ D32Params p, const int grid_mode) {
     MSDA_TICK(0);
     __syncthreads();                 // sample records, anchor sums, G, the next unit's slot
     MSDA_TICK(5);
-    tile_sort<VT, GT>(p, slot, more ? (slot ^ 1) : -1, grid_mode);
+    tile_sort(p, more ? (slot ^ 1) : -1, grid_mode);
     MSDA_TICK(1);
     __syncthreads();                 // entries and key list complete
     MSDA_TICK(5);
