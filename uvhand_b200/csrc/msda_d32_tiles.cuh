@@ -47,7 +47,8 @@ namespace msda {
 #define MSDA_TILE_EXPERIMENT 0
 #endif
 #ifndef MSDA_TILE_WAVES
-#define MSDA_TILE_WAVES 4     // grid = 2 resident CTAs per SM x this many; CTAs stride over the units
+#define MSDA_TILE_WAVES 8     // grid = 2 resident CTAs per SM x this many; CTAs stride over the units (2 / 4 / 8 / 16:
+                              // 424 / 420 / 404 / 406 us at C2: shorter CTAs let the hardware balance the tail)
 #endif
 
 constexpr int kTileQ = 64;                        // queries per unit
@@ -58,7 +59,14 @@ constexpr int kTileL = 4;
 constexpr int kTileSamples = kTileQ * kTileLP;    // 1024: two per thread
 constexpr int kTileEntries = kTileSamples * 2;    // 2048 row-pair contributions at most (two per sample)
 constexpr int kTileDots = kTileSamples * 4;       // one dot product per bilinear corner
-constexpr int kWinDim = 20;                       // window edge per level when the pyramid is large
+#ifndef MSDA_TILE_WIN
+#define MSDA_TILE_WIN 20
+#endif
+#ifndef MSDA_TILE_STATIC_4THS
+#define MSDA_TILE_STATIC_4THS 2   // share of the key passes handed out statically, the rest through a shared counter
+                                  // (0 / 1 / 2 / 3 / 4 quarters: 414 / 397* / 405 / 420 / 414 us at C2; * with 8 waves)
+#endif
+constexpr int kWinDim = MSDA_TILE_WIN;            // window edge per level when the pyramid is large
 constexpr int kRowCap = 1664;                     // window keys (4 levels x 20 x 20, or a whole small pyramid)
 constexpr int kWholeMaxRows = 1500;               // host side: pyramids up to this many tokens are expected to be windowed whole
 constexpr int kWholeMaxKeys = kRowCap;            // device side: ... when their H x (W + 1) keys fit the table
@@ -450,11 +458,11 @@ __device__ __noinline__ void tile_keys(const void* value, void* grad_value, unsi
   const unsigned gb_base = (unsigned)__cvta_generic_to_shared(sh.G + (first ^ 4));
   const unsigned ent_base = (unsigned)__cvta_generic_to_shared(sh.entries);
   const unsigned dot_base = (unsigned)__cvta_generic_to_shared(sh.dbuf) + (unsigned)(h >> 1) * 4u;
-  // Passes (8 keys each): the first three quarters go to the warps in serpentine order (lists are sorted by length,
+  // Passes (8 keys each): the first half goes to the warps in serpentine order (lists are sorted by length,
   // so straight round robin would hand warp 0 the longest pass of every round), the rest is handed out by a
   // shared counter so that the warps reach the barrier together.
   const int n_pass = (n_rows + kBatchRows - 1) / kBatchRows;
-  const int static_rounds = (n_pass / kTileWarps) * 3 / 4;
+  const int static_rounds = (n_pass / kTileWarps) * MSDA_TILE_STATIC_4THS / 4;
   int round = 0;
   for (;;) {
     int cur;
