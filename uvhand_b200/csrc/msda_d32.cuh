@@ -473,13 +473,26 @@ bwd_d32_kernel(const D32Params p) {
 #pragma unroll
         for (int q4 = 0; q4 < (kStatic ? kP / 4 : 1); ++q4) {
           const int s0 = l * kP + q4 * 4;
-          float pa[4], px[4], py[4];
+          // Transposed reduction of the 4 samples' (weight, x, y) partial sums over the 8 lanes, taken in two halves
+          // (samples 0 + 2, then 1 + 3: the pairs the first exchange step combines) so that at most six partial sums
+          // are alive next to a sample's four value chunks -- the all-at-once form spilled inside this loop.
+          const bool hi4 = sub & 4, hi2 = sub & 2;
+          float ra[2], rx[2], ry[2];
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            bwd_sample<VT, GT>(my_recs[s0 + j], vb, gvb, g, M, wm, Wf, Hf, live, pa[j], px[j], py[j]);
-          const float ta = group8_sum4(pa, sub);
-          const float tx = group8_sum4(px, sub);
-          const float ty = group8_sum4(py, sub);
+          for (int hlf = 0; hlf < 2; ++hlf) {
+            float pa0, px0, py0, pa2, px2, py2;
+            bwd_sample<VT, GT>(my_recs[s0 + hlf], vb, gvb, g, M, wm, Wf, Hf, live, pa0, px0, py0);
+            bwd_sample<VT, GT>(my_recs[s0 + hlf + 2], vb, gvb, g, M, wm, Wf, Hf, live, pa2, px2, py2);
+            ra[hlf] = (hi4 ? pa2 : pa0) + __shfl_xor_sync(kFull, hi4 ? pa0 : pa2, 4);
+            rx[hlf] = (hi4 ? px2 : px0) + __shfl_xor_sync(kFull, hi4 ? px0 : px2, 4);
+            ry[hlf] = (hi4 ? py2 : py0) + __shfl_xor_sync(kFull, hi4 ? py0 : py2, 4);
+          }
+          float ta = (hi2 ? ra[1] : ra[0]) + __shfl_xor_sync(kFull, hi2 ? ra[0] : ra[1], 2);
+          float tx = (hi2 ? rx[1] : rx[0]) + __shfl_xor_sync(kFull, hi2 ? rx[0] : rx[1], 2);
+          float ty = (hi2 ? ry[1] : ry[0]) + __shfl_xor_sync(kFull, hi2 ? ry[0] : ry[1], 2);
+          ta += __shfl_xor_sync(kFull, ta, 1);
+          tx += __shfl_xor_sync(kFull, tx, 1);
+          ty += __shfl_xor_sync(kFull, ty, 1);
           const int s = s0 + (sub >> 1);
           if (!kFuse) {
             if (live) {
