@@ -20,6 +20,7 @@ ap.add_argument("--kind", default="f32")
 ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--fwd-path", type=int, default=0)
 ap.add_argument("--bwd-path", type=int, default=0)
+ap.add_argument("--opts", default="", help="comma-separated key=value library options")
 a = ap.parse_args()
 
 wl = WORKLOADS[a.workload]
@@ -32,6 +33,9 @@ ga = torch.empty_like(sets[0]["aw"])
 scratch = torch.zeros(gv.shape, device="cuda") if a.kind == "bf16" else None
 cabi.set_option("fwd_path", a.fwd_path)
 cabi.set_option("bwd_path", a.bwd_path)
+for kv in filter(None, a.opts.split(",")):
+    k, v = kv.split("=")
+    cabi.set_option(k, int(v))
 st = torch.cuda.current_stream().cuda_stream
 torch.cuda.synchronize()
 for i in range(a.steps):
