@@ -1045,6 +1045,33 @@ def test_tile_backward_when_its_windows_miss():
     check_all(res, oracle(x["value"], x["shapes"], x["lsi"], x["loc"], x["aw"], x["grad_out"]))
 
 
+@pytest.mark.parametrize("levels,lsi,S", [
+    # tokens nobody's level owns at both ends and between the levels; levels stored out of order
+    (((20, 27), (10, 14), (5, 7), (3, 4)), (40, 620, 800, 580), 877),
+    # the same with a pyramid too large to be windowed whole (8x8 pixel tiles with moving windows)
+    (((40, 57), (20, 29), (10, 15), (5, 8)), (2300, 1500, 100, 0), 4700),
+    # two levels that overlap in `value` (legal for the operator: the levels are just views)
+    (((20, 27), (10, 14), (5, 7), (3, 4)), (0, 300, 300, 0), 540),
+])
+def test_tile_backward_with_irregular_level_layout(levels, lsi, S):
+    """Lq == S selects the pixel-block tile backward, which ASSUMES query i sits at token i's pixel only to place its
+    windows: whatever level_start_index says (gaps, other orders, overlapping levels, tokens beyond the pyramid),
+    every query in [0, Lq) must be processed exactly once (the operator itself never checks the layout: cuh:258-297)."""
+    N, M, D, L, P = 2, 8, 32, 4, 4
+    rng = np.random.default_rng(S)
+    x = {
+        "value": rng.standard_normal((N, S, M, D), dtype=np.float32),
+        "shapes": np.asarray(levels, np.int64), "lsi": np.asarray(lsi, np.int64),
+        "loc": rng.random((N, S, M, L, P, 2), dtype=np.float32) * 1.2 - 0.1,
+        "aw": rng.random((N, S, M, L, P), dtype=np.float32),
+        "grad_out": rng.standard_normal((N, S, M * D), dtype=np.float32),
+    }
+    with Paths(0, 0, 1, 2, 1):
+        res = run_cabi("f32", x["value"], x["shapes"], x["lsi"], x["loc"], x["aw"], x["grad_out"])
+    assert res["bwd_path"] == "bwd_d32_tiles_f32"
+    check_all(res, oracle(x["value"], x["shapes"], x["lsi"], x["loc"], x["aw"], x["grad_out"]))
+
+
 def test_backward_with_no_value_tokens_writes_zero_gradients():
     """S == 0: msda_bwd_* promise grad_sampling_loc / grad_attn_weight 'fully written' (include/msda_b200.h)."""
     N, M, D, L, Lq, P = 2, 8, 32, 4, 5, 4

@@ -98,7 +98,8 @@ struct TileShared {
   int wsum[kTileWarps];
   LevelTab tab;
   int ww[kTileL], wh[kTileL], wbase[kTileL + 1], fixed[kTileL];
-  int tile0[kTileL + 1], tiles_x[kTileL];
+  int tile0[kTileL + 2], tiles_x[kTileL];   // first tile of each level's pixel blocks, of the linear tail, and the count
+  int qstart[kTileL + 1];                   // first query of each level's blocks (from the shapes alone), then of the tail
   int anchor_sum[kTileL][3];            // sum (w_low + 1), sum (h_low + 1), count of accepted samples per level
   TileUnit unit[2];                     // this unit and the next one (alternating)
   int n_left, n_win, n_vrows, n_tiles, all_fixed, next_pass;
@@ -125,8 +126,13 @@ __device__ __forceinline__ TileShared& tile_smem() {
   return *reinterpret_cast<TileShared*>(smem_raw);
 }
 
-// unit -> (head, sample, tile origin).  grid mode: tile = an 8x8 pixel block of one level (query i is token i);
-// linear mode: 64 consecutive queries.
+// unit -> (head, sample, tile origin).  grid mode: tile = an 8x8 pixel block of one level, then 64-query pieces of the
+// queries beyond the pyramid (lq == kTileL); linear mode: 64 consecutive queries.
+// The pixel blocks are enumerated from the level SHAPES alone -- query qstart[l] + y * W_l + x, qstart = running sum of
+// H * W -- so every query in [0, Lq) belongs to exactly one unit whatever level_start_index says (gaps, other orders,
+// overlapping levels: the operator never checks the layout, cuh:258-297).  When the queries ARE the pyramid's tokens in
+// the usual layout (the encoder) the blocks are pixel blocks and their samples fall into the unit's windows; otherwise
+// the windows just catch less.
 __device__ __forceinline__ void decode_unit(TileShared& sh, int slot, int grid_mode, unsigned u, unsigned n_tiles,
                                             int M) {
   TileUnit d;
@@ -135,13 +141,18 @@ __device__ __forceinline__ void decode_unit(TileShared& sh, int slot, int grid_m
   const int tile = (int)(um % n_tiles);
   d.b = (int)(um / n_tiles);
   if (!grid_mode) {
-    d.lq = 0; d.y0 = 0; d.x0 = tile * kTileQ;
+    d.lq = kTileL; d.y0 = 0; d.x0 = tile * kTileQ;
   } else {
-    d.lq = (tile >= sh.tile0[1]) + (tile >= sh.tile0[2]) + (tile >= sh.tile0[3]);
+    d.lq = (tile >= sh.tile0[1]) + (tile >= sh.tile0[2]) + (tile >= sh.tile0[3]) + (tile >= sh.tile0[4]);
     const int tt = tile - sh.tile0[d.lq];
-    const int ty = tt / sh.tiles_x[d.lq];
-    d.y0 = ty * 8;
-    d.x0 = (tt - ty * sh.tiles_x[d.lq]) * 8;
+    if (d.lq == kTileL) {
+      d.y0 = 0;
+      d.x0 = sh.qstart[kTileL] + tt * kTileQ;
+    } else {
+      const int ty = tt / sh.tiles_x[d.lq];
+      d.y0 = ty * 8;
+      d.x0 = (tt - ty * sh.tiles_x[d.lq]) * 8;
+    }
   }
   d.pad[0] = d.pad[1] = d.pad[2] = 0;
   sh.unit[slot] = d;
@@ -158,15 +169,18 @@ __device__ __forceinline__ void cp_async_16(void* smem, const void* gmem) {
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-// query index of local slot (ql; pixel dy, dx of the 8x8 block in grid mode) of a unit's tile, or -1
+// query index of local slot (ql; pixel dy, dx of the 8x8 block) of a unit's tile, or -1
 __device__ __forceinline__ int unit_query(const TileShared& sh, const TileUnit& un, int grid_mode, int Lq, int ql, int dy,
                                           int dx) {
-  if (!grid_mode) {
-    const int q = un.x0 + ql;
-    return q < Lq ? q : -1;
+  int q;
+  if (un.lq == kTileL) {
+    q = un.x0 + ql;
+  } else {
+    const int y = un.y0 + dy, x = un.x0 + dx, W = sh.tab.W[un.lq];
+    if (y >= sh.tab.H[un.lq] || x >= W) return -1;
+    q = sh.qstart[un.lq] + y * W + x;
   }
-  const int y = un.y0 + dy, x = un.x0 + dx, W = sh.tab.W[un.lq];
-  return (y < sh.tab.H[un.lq] && x < W) ? sh.tab.start[un.lq] + y * W + x : -1;
+  return q < Lq ? q : -1;
 }
 
 // Asynchronous copies of a unit's inputs: every thread copies exactly what it will read itself (its two samples),
@@ -651,7 +665,7 @@ bwd_d32_tile_kernel(const __grid_constant__ D32Params p, const int grid_mode) {
     int keys_whole = 0;
     for (int l = 0; l < kTileL; ++l) keys_whole += sh.tab.H[l] * (sh.tab.W[l] + 1);
     const bool whole = keys_whole <= kWholeMaxKeys;
-    int base = 0, tiles = 0, all_fixed = 1;
+    int base = 0, tiles = 0, all_fixed = 1, q0 = 0;
     for (int l = 0; l < kTileL; ++l) {
       const int H = sh.tab.H[l], W = sh.tab.W[l];
       const int ww = whole ? W + 1 : min(W + 1, kWinDim), wh = whole ? H : min(H, kWinDim);
@@ -660,12 +674,20 @@ bwd_d32_tile_kernel(const __grid_constant__ D32Params p, const int grid_mode) {
       all_fixed &= sh.fixed[l];
       base += ww * wh;
       sh.tile0[l] = tiles;
+      sh.qstart[l] = q0;
       sh.tiles_x[l] = (W + 7) >> 3;
-      tiles += ((W + 7) >> 3) * ((H + 7) >> 3);
+      // a level whose pixels do not all fit into the query range gets no blocks: its queries go to the linear tail
+      if (grid_mode && H > 0 && W > 0 && (long long)q0 + (long long)H * W <= p.Lq) {
+        q0 += H * W;
+        tiles += ((W + 7) >> 3) * ((H + 7) >> 3);
+      }
     }
     sh.wbase[kTileL] = base;
     sh.tile0[kTileL] = tiles;
-    sh.n_tiles = grid_mode ? tiles : (p.Lq + kTileQ - 1) / kTileQ;
+    sh.qstart[kTileL] = q0;
+    tiles += (p.Lq - q0 + kTileQ - 1) / kTileQ;      // linear mode: q0 == 0, every tile is one of these
+    sh.tile0[kTileL + 1] = tiles;
+    sh.n_tiles = tiles;
     sh.all_fixed = all_fixed;
     sh.n_left = 0;
     sh.next_pass = 0;
