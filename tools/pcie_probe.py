@@ -1,31 +1,57 @@
-"""PCIe probe: pinned host <-> device copy rates, one direction and both at once, for one 160 MB copy and for
-the same bytes cut into chunks (what the host pipeline of msda_host_fwd_bwd_f32 issues)."""
-import time
+#!/usr/bin/env python
+"""Host<->device copy rates of this box with pinned buffers (the bound of bench.py's e2e line).
+    python tools/pcie_probe.py [--mb 159]"""
+import argparse
 import torch
-n = 160 * 1024 * 1024 // 4
-h = torch.empty(n, dtype=torch.float32).pin_memory(); h2 = torch.empty(n, dtype=torch.float32).pin_memory()
-d = torch.empty(n, device="cuda"); d2 = torch.empty(n, device="cuda")
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--mb", type=float, default=159.3)
+a = ap.parse_args()
+n = int(a.mb * 1e6)
+h_in = torch.empty(n, dtype=torch.uint8).pin_memory()
+h_out = torch.empty(n, dtype=torch.uint8).pin_memory()
+d_in = torch.empty(n, dtype=torch.uint8, device="cuda")
+d_out = torch.empty(n, dtype=torch.uint8, device="cuda")
 s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
 
 
-def t(fn, k=5):
-    fn(); torch.cuda.synchronize(); t0 = time.perf_counter()
-    for _ in range(k):
+def timed(fn, reps=10):
+    fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
         fn()
-    torch.cuda.synchronize(); return (time.perf_counter() - t0) / k
+    s1.synchronize(); s2.synchronize()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
 
 
-for mb in (160, 16, 4, 1):
-    c = mb * 1024 * 1024 // 4
-    def up():
-        with torch.cuda.stream(s1):
-            for o in range(0, n, c):
-                d[o:o + c].copy_(h[o:o + c], non_blocking=True)
-    def down():
-        with torch.cuda.stream(s2):
-            for o in range(0, n, c):
-                h2[o:o + c].copy_(d2[o:o + c], non_blocking=True)
-    def both():
-        up(); down()
-    a, b, e = t(up), t(down), t(both)
-    print(f"copies of {mb:4d} MiB: H2D {160/1024/a:5.1f} GiB/s  D2H {160/1024/b:5.1f} GiB/s  both at once {e*1e3:5.2f} ms -> {160/1024/e:5.1f} GiB/s each")
+def h2d(chunks=1):
+    with torch.cuda.stream(s1):
+        s1.wait_stream(torch.cuda.current_stream())
+        for c in range(chunks):
+            lo, hi = c * n // chunks, (c + 1) * n // chunks
+            d_in[lo:hi].copy_(h_in[lo:hi], non_blocking=True)
+        torch.cuda.current_stream().wait_stream(s1)
+
+
+def d2h(chunks=1):
+    with torch.cuda.stream(s2):
+        s2.wait_stream(torch.cuda.current_stream())
+        for c in range(chunks):
+            lo, hi = c * n // chunks, (c + 1) * n // chunks
+            h_out[lo:hi].copy_(d_out[lo:hi], non_blocking=True)
+        torch.cuda.current_stream().wait_stream(s2)
+
+
+def both(chunks=1):
+    h2d(chunks)
+    d2h(chunks)
+
+
+for name, fn in (("H2D alone", h2d), ("D2H alone", d2h), ("both directions at once", both),
+                 ("both, 16 chunks each", lambda: both(16)), ("both, 64 chunks each", lambda: both(64))):
+    ms = timed(fn)
+    print(f"{name:28s} {ms:7.3f} ms  {n / ms / 1e6:6.1f} GB/s per direction")
