@@ -13,6 +13,7 @@ h_out = torch.empty(n, dtype=torch.uint8).pin_memory()
 d_in = torch.empty(n, dtype=torch.uint8, device="cuda")
 d_out = torch.empty(n, dtype=torch.uint8, device="cuda")
 s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+s3, s4 = torch.cuda.Stream(), torch.cuda.Stream()
 
 
 def timed(fn, reps=10):
@@ -22,7 +23,7 @@ def timed(fn, reps=10):
     e0.record()
     for _ in range(reps):
         fn()
-    s1.synchronize(); s2.synchronize()
+    s1.synchronize(); s2.synchronize(); s3.synchronize(); s4.synchronize()
     e1.record()
     torch.cuda.synchronize()
     return e0.elapsed_time(e1) / reps
@@ -46,12 +47,30 @@ def d2h(chunks=1):
         torch.cuda.current_stream().wait_stream(s2)
 
 
+def both2(chunks):
+    """two streams per direction, chunks alternating between them"""
+    cur = torch.cuda.current_stream()
+    for st in (s1, s2, s3, s4):
+        st.wait_stream(cur)
+    for c in range(chunks):
+        lo, hi = c * n // chunks, (c + 1) * n // chunks
+        with torch.cuda.stream(s1 if c & 1 else s3):
+            d_in[lo:hi].copy_(h_in[lo:hi], non_blocking=True)
+        with torch.cuda.stream(s2 if c & 1 else s4):
+            h_out[lo:hi].copy_(d_out[lo:hi], non_blocking=True)
+    for st in (s1, s2, s3, s4):
+        cur.wait_stream(st)
+
+
 def both(chunks=1):
     h2d(chunks)
     d2h(chunks)
 
 
 for name, fn in (("H2D alone", h2d), ("D2H alone", d2h), ("both directions at once", both),
-                 ("both, 16 chunks each", lambda: both(16)), ("both, 64 chunks each", lambda: both(64))):
+                 ("both, 16 chunks each", lambda: both(16)), ("both, 64 chunks each", lambda: both(64)),
+                 ("H2D alone, 16 chunks", lambda: h2d(16)), ("D2H alone, 16 chunks", lambda: d2h(16)),
+                 ("both, 16 chunks, 2 streams per direction", lambda: both2(16)),
+                 ("both, 64 chunks, 2 streams per direction", lambda: both2(64))):
     ms = timed(fn)
     print(f"{name:28s} {ms:7.3f} ms  {n / ms / 1e6:6.1f} GB/s per direction")

@@ -183,7 +183,7 @@ int launch_fwd_d32(D32Params& p, cudaStream_t st, bool* split = nullptr, bool* w
     if (wide) *wide = true;
     return finish_launch(1);
   }
-  const int grid = d32_grid(p.n_items, MSDA_FWD_MINB, sizeof(VT) == 4 ? MSDA_FWD_WAVES : MSDA_FWD_WAVES_BF16);
+  const int grid = d32_grid(p.n_items, kFuse ? MSDA_FWD_FUSE_MINB : MSDA_FWD_MINB, sizeof(VT) == 4 ? MSDA_FWD_WAVES : MSDA_FWD_WAVES_BF16);
   if (p.L == 4 && p.P == 4 && p.M == 8) {   // the shipped geometry (util/settings.py:102-120)
     fwd_d32_kernel<VT, 4, 4, 8, kFuse><<<grid, kD32Threads, d32_smem(LP), st>>>(p);
   } else if (p.L == 4 && p.P == 4) {        // same sampling pattern, another head count

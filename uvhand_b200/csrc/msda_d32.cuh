@@ -42,6 +42,12 @@ namespace msda {
 #ifndef MSDA_BWD_MINB
 #define MSDA_BWD_MINB 4
 #endif
+// The fused-prologue forward carries the softmax / location arithmetic in phase A: at 40 registers it spills
+// 112 B per thread; 4 CTAs per SM (64 registers, no spills) measured fastest (C2 194 -> 179 us, C3 encoder 136 -> 126;
+// 5 CTAs 188 / 131, 3 CTAs 188 / 132).
+#ifndef MSDA_FWD_FUSE_MINB
+#define MSDA_FWD_FUSE_MINB 4
+#endif
 // Tuning switches, defaults = what measured fastest on B200 at the DETR-encoder shape
 // (gpurun_out A/B logs summarised in profiles/r01_tuning_matrix.md):
 //   *_PREFETCH  software-pipelined phase A (next pass's locations/weights requested before the gathers)
@@ -148,6 +154,10 @@ __device__ __forceinline__ int4 make_record(float x, float y, float a, int H, in
 __device__ __forceinline__ float2 fused_location(const D32Params& p, long long item, int l, float2 off,
                                                  int H, int W) {
   const float2 r = __ldg(reinterpret_cast<const float2*>(p.ref) + (item / p.M) * p.L + l);
+  return make_float2(__fadd_rn(r.x, __fdiv_rn(off.x, (float)W)), __fadd_rn(r.y, __fdiv_rn(off.y, (float)H)));
+}
+// the same with the reference point already on chip
+__device__ __forceinline__ float2 fused_location(float2 r, float2 off, int H, int W) {
   return make_float2(__fadd_rn(r.x, __fdiv_rn(off.x, (float)W)), __fadd_rn(r.y, __fdiv_rn(off.y, (float)H)));
 }
 
@@ -279,7 +289,7 @@ struct LevelStride {
 // Forward
 // ---------------------------------------------------------------------------------------------
 template <typename VT, int kL, int kP, int kM, bool kFuse = false>  // compile-time levels / points / heads (0: runtime)
-__global__ void __launch_bounds__(kD32Threads, MSDA_FWD_MINB)
+__global__ void __launch_bounds__(kD32Threads, kFuse ? MSDA_FWD_FUSE_MINB : MSDA_FWD_MINB)
 fwd_d32_kernel(const D32Params p) {
   using C = Chunk<VT>;
   using Vec = typename C::Vec;

@@ -90,6 +90,7 @@ struct TileShared {
   int hw[kTileSamples];                 // h_low << 16 | (w_low & 0xffff) per sample (4 KB)
   float2 stage_loc[kTileSamples];       // the NEXT unit's sampling locations / weights, copied asynchronously while
   float stage_aw[kTileSamples];         // this unit is processed (12 KB): their HBM latency never heads a unit
+  float2 stage_ref[kTileQ * kTileL];    // fused prologue: the next unit's reference points, one per (query, level) (2 KB)
   int off[kRowCap + 8];                 // counts per key; then exclusive offsets
   int rowtok[kRowCap + 8];              // (token * M of the key's LEFT row) << 2 | right row exists << 1 | left row exists,
                                         // of every touched window key
@@ -199,6 +200,11 @@ __device__ __noinline__ void request_samples(const D32Params& p, int slot, int g
       cp_async_4(&sh.stage_aw[t + kTileThreads * i], p.aw + gs);
     }
   }
+  if (p.ref != nullptr && t < kTileQ * kTileL) {   // fused prologue (read by other threads: tile_geometry has the barrier)
+    const int ql = t >> 2;
+    const int q = unit_query(sh, un, grid_mode, p.Lq, ql, ql >> 3, ql & 7);
+    if (q >= 0) cp_async_8(&sh.stage_ref[t], reinterpret_cast<const float2*>(p.ref) + ((qbase + q) * kTileL + (t & 3)));
+  }
 }
 __device__ __noinline__ void request_grad_rows(const D32Params& p, int slot, int grid_mode) {
   TileShared& sh = tile_smem();
@@ -230,8 +236,8 @@ __device__ __noinline__ void tile_geometry(const D32Params& p, int slot, int gri
   const int lp = t & 15, l = lp >> 2;
   const TileUnit un = sh.unit[slot];
   const int Hl = sh.tab.H[l], Wl = sh.tab.W[l];
-  const unsigned qbase = (unsigned)un.b * (unsigned)p.Lq;
   cp_async_wait_all();         // this thread's own copies (its samples, its chunk of G) have landed
+  if (kFuse) __syncthreads();  // ... and the reference points, which other threads copied
   int packed = 0, accepted = 0;
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
@@ -246,7 +252,7 @@ __device__ __noinline__ void tile_geometry(const D32Params& p, int slot, int gri
     if (q >= 0) {
       float2 xy = sh.stage_loc[t + kTileThreads * i];
       if (kFuse) {
-        xy = fused_location(p, (long long)(qbase + q) * p.M + un.m, l, xy, Hl, Wl);
+        xy = fused_location(sh.stage_ref[((t >> 4) + 32 * i) * kTileL + l], xy, Hl, Wl);
         aw = a;                     // the softmax backward needs the weight of rejected samples too
       }
       SampleGeom<float> g;
