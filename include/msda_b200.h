@@ -197,7 +197,9 @@ int msda_host_fwd_bwd_bf16(msda_host_plan *plan, const uint16_t *value, const in
  * the SM (num_levels = num_point = 4): 0 = chosen by shape (encoder self-attention num_query == spatial_size, or a
  * pyramid of at most 1500 tokens), 1 = never, 2 = whenever the shape is eligible; "fwd_wide": the forward with 4 lanes
  * per (query, head) and 8 channels per lane (num_levels = num_point = 4): 0 = for bf16 values, 1 = never, 2 = also for
- * fp32 values.  None of these changes results
+ * fp32 values; "fwd_slab": the fp32 forward that stages one head of one sample in shared memory and gathers from there
+ * (num_levels = num_point = 4, spatial_size <= 1600): 0 = when the call has at least two 64-query passes per SM,
+ * 1 = never, 2 = whenever the shape is eligible.  None of these changes results
  * beyond summation order.  Options are process-global (every thread and stream sees them); they exist for tests and
  * benchmarks, production callers leave them at 0.
  * Returns MSDA_OK or MSDA_ERR_BAD_OPTION. */

@@ -93,7 +93,7 @@ def test_argument_validation_without_gpu():
 
 
 def test_options_roundtrip():
-    for key in ("fwd_path", "bwd_path", "split_mode", "bwd_tiles", "fwd_wide"):
+    for key in ("fwd_path", "bwd_path", "split_mode", "bwd_tiles", "fwd_wide", "fwd_slab"):
         assert cabi.get_option(key) == 0
         cabi.set_option(key, 1)
         assert cabi.get_option(key) == 1

@@ -43,10 +43,11 @@ class Paths:
     """Context manager forcing a kernel family.  fwd/bwd: 0 auto, 1 any-shape kernels;
     split: 0 auto (by problem size), 1 never (4 items per warp), 2 always (1 item per warp);
     tiles: the on-chip-combining backward (L = P = 4): 0 by shape, 1 never, 2 whenever the shape is eligible;
-    wide: the 8-channels-per-lane forward (L = P = 4): 0 / 2 whenever eligible and not split, 1 never."""
+    wide: the 8-channels-per-lane forward (L = P = 4): 0 / 2 whenever eligible and not split, 1 never;
+    slab: the shared-memory slab forward (fp32, L = P = 4, S <= 1600): 0 by shape, 1 never, 2 whenever eligible."""
 
-    def __init__(self, fwd=0, bwd=0, split=0, tiles=1, wide=1):
-        self.f, self.b, self.s, self.t, self.w = fwd, bwd, split, tiles, wide
+    def __init__(self, fwd=0, bwd=0, split=0, tiles=1, wide=1, slab=1):
+        self.f, self.b, self.s, self.t, self.w, self.sl = fwd, bwd, split, tiles, wide, slab
 
     def __enter__(self):
         cabi.set_option("fwd_path", self.f)
@@ -54,6 +55,7 @@ class Paths:
         cabi.set_option("split_mode", self.s)
         cabi.set_option("bwd_tiles", self.t)
         cabi.set_option("fwd_wide", self.w)
+        cabi.set_option("fwd_slab", self.sl)
 
     def __exit__(self, *a):
         cabi.set_option("fwd_path", 0)
@@ -61,10 +63,12 @@ class Paths:
         cabi.set_option("split_mode", 0)
         cabi.set_option("bwd_tiles", 0)
         cabi.set_option("fwd_wide", 0)
+        cabi.set_option("fwd_slab", 0)
 
 
 # the kernel families every parity case runs through (D = 32 shapes; "tiles" applies to L = P = 4 only)
-FAMILIES = {"d32": (0, 0, 1, 1, 1), "split": (0, 0, 2, 1, 1), "tiles": (0, 0, 1, 2, 2), "anyshape": (1, 1, 0, 1, 1)}
+FAMILIES = {"d32": (0, 0, 1, 1, 1), "split": (0, 0, 2, 1, 1), "tiles": (0, 0, 1, 2, 2), "slab": (0, 0, 1, 1, 1, 2),
+            "anyshape": (1, 1, 0, 1, 1)}
 FAMILY_IDS = list(FAMILIES)
 
 
@@ -134,6 +138,7 @@ def test_golden_f32(path, forced):
         l4p4 = g["loc"].shape[3] == 4 and g["loc"].shape[4] == 4
         want = {"d32": ("fwd_d32_f32", "bwd_d32_f32"), "split": ("fwd_d32_split_f32", "bwd_d32_split_f32"),
                 "tiles": ("fwd_d32_wide_f32" if l4p4 else "fwd_d32_f32", "bwd_d32_tiles_f32" if l4p4 else "bwd_d32_f32"),
+                "slab": ("fwd_d32_slab_f32" if l4p4 and g["value"].shape[1] <= 1600 else "fwd_d32_f32", "bwd_d32_f32"),
                 "anyshape": ("fwd_generic_f32", "bwd_generic_f32")}[forced]
         assert (res["fwd_path"], res["bwd_path"]) == want
 
@@ -422,7 +427,8 @@ def test_full_size_properties_f32(name):
     # the 900/1098-query decoders are small enough for the one-item-per-warp forward; their queries have no
     # relation to the (large) pyramid, so the backward reduces straight to L2.  Encoder self-attention and the
     # small ARCTIC pyramid take the on-chip-combining backward.
-    want = ("fwd_d32_split_f32" if name.startswith("c4") else "fwd_d32_f32",
+    # The small ARCTIC pyramid is gathered from a shared-memory slab in the forward.
+    want = ("fwd_d32_split_f32" if name.startswith("c4") else "fwd_d32_slab_f32" if name.startswith("c3") else "fwd_d32_f32",
             "bwd_d32_f32" if name.startswith("c4") else "bwd_d32_tiles_f32")
     assert (cabi.last_path(False), cabi.last_path(True)) == want
     g = t["grad_out"].view_as(out).double()

@@ -15,6 +15,7 @@ from uvhand_b200.workloads import WORKLOADS, encoder_reference_points, make_inpu
 ap = argparse.ArgumentParser()
 ap.add_argument("--workloads", default="c2_detr_encoder,c3_arctic_encoder")
 ap.add_argument("--iters", type=int, default=30)
+ap.add_argument("--no-gref", action="store_true", help="reference points do not need a gradient (the encoder)")
 a = ap.parse_args()
 st = torch.cuda.current_stream().cuda_stream
 for name in a.workloads.split(","):
@@ -43,7 +44,7 @@ for name in a.workloads.split(","):
         e[1].record()
         cabi.fused_backward(x["grad_out"].data_ptr(), x["value"].data_ptr(), x["shapes"].data_ptr(), x["lsi"].data_ptr(),
                             x["ref"].data_ptr(), x["off"].data_ptr(), x["logits"].data_ptr(), wl.dims(), gv.data_ptr(),
-                            goff.data_ptr(), glog.data_ptr(), gref.data_ptr(), st)
+                            goff.data_ptr(), glog.data_ptr(), None if a.no_gref else gref.data_ptr(), st)
         e[2].record()
         torch.cuda.synchronize()
         if it >= 5:

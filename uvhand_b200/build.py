@@ -56,7 +56,7 @@ def _run(cmd, verbose):
 
 
 def cabi_sources():
-    return [os.path.join(CSRC, f) for f in ("msda_b200.cu", "msda_device.cuh", "msda_generic.cuh", "msda_d32.cuh", "msda_d32_tiles.cuh", "msda_d32_wide.cuh")] + [
+    return [os.path.join(CSRC, f) for f in ("msda_b200.cu", "msda_device.cuh", "msda_generic.cuh", "msda_d32.cuh", "msda_d32_tiles.cuh", "msda_d32_wide.cuh", "msda_d32_slab.cuh")] + [
         os.path.join(ROOT, "include", "msda_b200.h")]
 
 

@@ -16,6 +16,7 @@
 #include "msda_d32.cuh"
 #include "msda_d32_tiles.cuh"
 #include "msda_d32_wide.cuh"
+#include "msda_d32_slab.cuh"
 #include "msda_generic.cuh"
 
 namespace {
@@ -26,6 +27,7 @@ std::atomic<int> g_fwd_path{0};
 std::atomic<int> g_bwd_path{0};
 std::atomic<int> g_bf16_direct{0};
 std::atomic<int> g_split_mode{0};   // 0 auto, 1 never, 2 always
+std::atomic<int> g_fwd_slab{0};     // shared-memory slab forward for small pyramids (fp32, L = P = 4): 0 by shape, 1 never, 2 whenever eligible
 std::atomic<int> g_fwd_wide{0};     // 8-channels-per-lane forward (L = P = 4): 0 by shape, 1 never, 2 whenever eligible
 std::atomic<int> g_bwd_tiles{0};    // on-chip-combining backward (L = P = 4): 0 by shape, 1 never, 2 whenever eligible
 std::atomic<long long> g_launches{0};
@@ -155,7 +157,7 @@ int split_grid(long long n_items, int resident_per_sm) {
 constexpr size_t kSplitSmem = (size_t)kD32Warps * kMaxLPD32 * 16;
 
 template <typename VT, bool kFuse = false>
-int launch_fwd_d32(D32Params& p, cudaStream_t st, bool* split = nullptr, bool* wide = nullptr) {
+int launch_fwd_d32(D32Params& p, cudaStream_t st, bool* split = nullptr, bool* wide = nullptr, bool* slab = nullptr) {
   begin_call();
   const int LP = p.L * p.P;
   p.n_items = (long long)p.N * p.Lq * p.M;
@@ -165,6 +167,30 @@ int launch_fwd_d32(D32Params& p, cudaStream_t st, bool* split = nullptr, bool* w
   if (sp) {
     fwd_d32_split_kernel<VT, kFuse><<<split_grid(p.n_items, 4), kD32Threads, kSplitSmem, st>>>(p);
     return finish_launch(1);
+  }
+  // Small pyramid, fp32 rows: one head of one sample staged in shared memory, corner rows gathered with LDS.128
+  // (msda_d32_slab.cuh).  By shape when the call has at least two CTA passes (64 queries of one head) per SM.
+  if (sizeof(VT) == 4 && p.L == kSlabL && p.P == kSlabP && p.S <= kSlabMaxRows && p.n_items * kSlabLP < (1ll << 31)) {
+    const int slab_mode = g_fwd_slab.load();
+    const long long n_pass = (long long)p.N * p.M * ((p.Lq + kSlabPassQ - 1) / kSlabPassQ);
+    if (slab_mode == 2 || (slab_mode == 0 && n_pass >= 2ll * sm_count())) {
+      auto kernel = p.M == 8 ? fwd_d32_slab_kernel<8, kFuse> : fwd_d32_slab_kernel<0, kFuse>;
+      static std::atomic<int> attr_done[64][2];
+      int dev = 0;
+      cudaGetDevice(&dev);
+      const int slot = dev >= 0 && dev < 64 ? dev : 0;
+      if (!attr_done[slot][p.M == 8].load(std::memory_order_acquire)) {
+        const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                   (int)slab_smem_bytes(kSlabMaxRows));
+        if (e != cudaSuccess) return (int)e;
+        attr_done[slot][p.M == 8].store(1, std::memory_order_release);
+      }
+      const long long ctas = n_pass < sm_count() ? n_pass : sm_count();
+      kernel<<<(int)ctas, kSlabThreads, slab_smem_bytes(p.S), st>>>(p);
+      if (split) *split = false;
+      if (slab) *slab = true;
+      return finish_launch(1);
+    }
   }
   // 4 lanes per item, 8 items per warp pass (msda_d32_wide.cuh).  Chosen for bf16 values (64 B rows: one 128-bit load
   // moves eight rows; C2 forward 135 -> 111 us).  For fp32 rows it is slower than 8 lanes per item (184 vs 152 us: a
@@ -352,6 +378,11 @@ int msda_b200_set_option(const char* key, int value) {
     g_fwd_wide.store(value);
     return MSDA_OK;
   }
+  if (!strcmp(key, "fwd_slab")) {
+    if (value < 0 || value > 2) return MSDA_ERR_BAD_OPTION;
+    g_fwd_slab.store(value);
+    return MSDA_OK;
+  }
   return MSDA_ERR_BAD_OPTION;
 }
 
@@ -363,6 +394,7 @@ int msda_b200_get_option(const char* key, int* value) {
   if (!strcmp(key, "split_mode")) { *value = g_split_mode.load(); return MSDA_OK; }
   if (!strcmp(key, "bwd_tiles")) { *value = g_bwd_tiles.load(); return MSDA_OK; }
   if (!strcmp(key, "fwd_wide")) { *value = g_fwd_wide.load(); return MSDA_OK; }
+  if (!strcmp(key, "fwd_slab")) { *value = g_fwd_slab.load(); return MSDA_OK; }
   return MSDA_ERR_BAD_OPTION;
 }
 
@@ -395,9 +427,9 @@ int msda_fwd_f32(const float* value, const int64_t* shapes, const int64_t* lsi, 
     D32Params p{};
     p.value = value; p.shapes = shapes; p.lsi = lsi; p.loc = loc; p.aw = aw; p.out = out;
     p.N = N; p.S = S; p.M = M; p.L = L; p.Lq = Lq; p.P = P;
-    bool sp = false, wide = false;
-    rc = launch_fwd_d32<float>(p, st, &sp, &wide);
-    g_last_path[0] = sp ? "fwd_d32_split_f32" : wide ? "fwd_d32_wide_f32" : "fwd_d32_f32";
+    bool sp = false, wide = false, slab = false;
+    rc = launch_fwd_d32<float>(p, st, &sp, &wide, &slab);
+    g_last_path[0] = sp ? "fwd_d32_split_f32" : slab ? "fwd_d32_slab_f32" : wide ? "fwd_d32_wide_f32" : "fwd_d32_f32";
     return rc;
   }
   g_last_path[0] = "fwd_generic_f32";
@@ -575,9 +607,9 @@ int msda_fused_fwd_f32(const float* value, const int64_t* shapes, const int64_t*
   D32Params p{};
   p.value = value; p.shapes = shapes; p.lsi = lsi; p.loc = offsets; p.aw = logits; p.ref = ref; p.out = out;
   p.N = N; p.S = S; p.M = M; p.L = L; p.Lq = Lq; p.P = P;
-  bool sp = false, wide = false;
-  rc = launch_fwd_d32<float, true>(p, st, &sp, &wide);
-  g_last_path[0] = sp ? "fwd_d32_split_fused_f32" : wide ? "fwd_d32_wide_fused_f32" : "fwd_d32_fused_f32";
+  bool sp = false, wide = false, slab = false;
+  rc = launch_fwd_d32<float, true>(p, st, &sp, &wide, &slab);
+  g_last_path[0] = sp ? "fwd_d32_split_fused_f32" : slab ? "fwd_d32_slab_fused_f32" : wide ? "fwd_d32_wide_fused_f32" : "fwd_d32_fused_f32";
   return rc;
 }
 
