@@ -25,7 +25,7 @@ for name in a.workloads.split(","):
     for seed in range(3):
         x = make_inputs(wl, seed=seed, device="cuda")
         x["ref"] = (encoder_reference_points(wl.levels, "cuda")[None, :, None, :].expand(N, Lq, L, 2).contiguous()
-                    if Lq == S else torch.rand(N, Lq, L, 2, device="cuda"))
+                    if Lq == S else (torch.rand(N, Lq, 1, 2, device="cuda") * 2 - 1).expand(N, Lq, L, 2).contiguous())   # "twostage"
         x["off"] = torch.randn(N, Lq, M, L, P, 2, device="cuda") * 2.0
         x["logits"] = torch.randn(N, Lq, M, L * P, device="cuda")
         sets.append(x)
