@@ -15,4 +15,9 @@ $P > $O/r02_prof_plain.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:d32 -s 2 -c 2 -o $O/r02_c2_f32 $P > $O/r02_prof_ncu.log 2>&1
 $P --kind bf16 > $O/r02_prof_plain_bf16.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:d32 -s 2 -c 2 -o $O/r02_c2_bf16 $P --kind bf16 > $O/r02_prof_ncu_bf16.log 2>&1
+# the slab forward at the ARCTIC encoder shape (BASELINE configs[2])
+P3="python tools/prof_run.py --workload c3_arctic_encoder --steps 2"
+$P3 > $O/r02_prof_plain_c3.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:slab -s 1 -c 1 -o $O/r02_c3_f32 $P3 > $O/r02_prof_ncu_c3.log 2>&1
+tail -n 2 $O/r02_prof_ncu_c3.log
 tail -n 2 $O/r02_prof_ncu.log $O/r02_prof_ncu_bf16.log $O/r02_launch_ncu.log
