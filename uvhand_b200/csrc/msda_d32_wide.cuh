@@ -19,8 +19,15 @@ namespace msda {
 #ifndef MSDA_FWD_WIDE_MINB
 #define MSDA_FWD_WIDE_MINB 4          // resident CTAs per SM (64 registers)
 #endif
+// Grid cap in units of "CTAs the device holds at once" and the one-pass-ahead request of the raw samples.  Measured at
+// C2 / C5 bf16 (us): 8 waves 111.5 / 1703 (round 2 until late), 1 wave (persistent warps, ~9 passes each) 106.5 / 1597,
+// 1 wave + prefetch 110.7 / 1664 (16 B of spills at 64 registers; 105.5 / 1596 at 3 CTAs per SM), 2 waves + prefetch
+// 114.8 / 1737; 1 wave at 3 / 5 / 6 CTAs per SM 106.5 / 114.9 / 114.7.
+#ifndef MSDA_FWD_WIDE_PREFETCH
+#define MSDA_FWD_WIDE_PREFETCH 0
+#endif
 #ifndef MSDA_FWD_WIDE_WAVES
-#define MSDA_FWD_WIDE_WAVES 8
+#define MSDA_FWD_WIDE_WAVES 1
 #endif
 
 constexpr int kWideItems = 8;          // items per warp pass
@@ -105,23 +112,31 @@ fwd_d32_wide_kernel(const D32Params p) {
 
   const long long n_pass = (p.n_items + kWideItems - 1) / kWideItems;
   const long long pass_stride = (long long)gridDim.x * kD32Warps;
-  for (long long pass = (long long)blockIdx.x * kD32Warps + warp; pass < n_pass; pass += pass_stride) {
+  // raw locations / weights of a pass: 8 items x 16 samples over 32 lanes (4 each), coalesced.  With MSDA_FWD_WIDE_PREFETCH
+  // the next pass's are requested before this pass starts gathering (their HBM latency then hides behind the gathers).
+  float2 xy[4];
+  float a[4];
+  auto load_raw = [&](long long ps) {
+    const long long s_base = ps * kWideItems * kWideLP, s_end = p.n_items * kWideLP;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const long long gs = s_base + lane + i * kWarp;
+      xy[i] = make_float2(0.f, 0.f);
+      a[i] = -INFINITY;
+      if (gs < s_end) {
+        xy[i] = ld_stream(reinterpret_cast<const float2*>(p.loc) + gs);
+        a[i] = ld_stream(p.aw + gs);
+      }
+    }
+  };
+  const long long pass0 = (long long)blockIdx.x * kD32Warps + warp;
+  if (MSDA_FWD_WIDE_PREFETCH && pass0 < n_pass) load_raw(pass0);
+  for (long long pass = pass0; pass < n_pass; pass += pass_stride) {
     const long long item0 = pass * kWideItems;
-    // ---- phase A: 8 items x 16 samples over 32 lanes (4 each), coalesced ----------------------------------
+    // ---- phase A ------------------------------------------------------------------------------------------------
     {
       const long long s_base = item0 * kWideLP, s_end = p.n_items * kWideLP;
-      float2 xy[4];
-      float a[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const long long gs = s_base + lane + i * kWarp;
-        xy[i] = make_float2(0.f, 0.f);
-        a[i] = -INFINITY;
-        if (gs < s_end) {
-          xy[i] = ld_stream(reinterpret_cast<const float2*>(p.loc) + gs);
-          a[i] = ld_stream(p.aw + gs);
-        }
-      }
+      if (!MSDA_FWD_WIDE_PREFETCH) load_raw(pass);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int s = lane + i * kWarp;
@@ -136,6 +151,7 @@ fwd_d32_wide_kernel(const D32Params p) {
         if (in)
           warp_recs[grp * kWideStride + ls] = make_record<false>(loc.x, loc.y, w, tab.H[l], tab.W[l], tab.start[l], M);
       }
+      if (MSDA_FWD_WIDE_PREFETCH && pass + pass_stride < n_pass) load_raw(pass + pass_stride);
     }
     __syncwarp();
 
