@@ -266,7 +266,14 @@ bool use_tiles(const D32Params& p) {
 template <typename VT, typename GT, bool kFuse = false>
 int launch_bwd_tiles(D32Params& p, cudaStream_t st) {
   begin_call();
-  const int grid_mode = p.Lq == p.S ? 1 : 0;
+  // Tiles: 8x8 pixel blocks for encoder self-attention on a large pyramid (the unit's windows must follow its queries);
+  // 64 consecutive queries otherwise -- also for self-attention on a pyramid small enough to be windowed whole, where
+  // the block shape buys nothing and the partly empty blocks at the level borders cost units (ARCTIC: 22 blocks of 64
+  // slots for 1045 queries against 17 linear tiles; C3 encoder backward 281 -> 252 us).
+#ifndef MSDA_TILE_LINEAR_WHOLE
+#define MSDA_TILE_LINEAR_WHOLE 1
+#endif
+  const int grid_mode = (p.Lq == p.S && !(MSDA_TILE_LINEAR_WHOLE && p.S <= kWholeMaxRows)) ? 1 : 0;
   auto kernel = bwd_d32_tile_kernel<VT, GT, kFuse>;
 #if MSDA_TILE_EXPERIMENT == 4 || defined(MSDA_TILE_ONE_PER_SM)   // timing experiment: one unit per SM
   const size_t smem = tile_smem_bytes() + 100 * 1024;
