@@ -1072,10 +1072,24 @@ def test_tile_backward_with_irregular_level_layout(levels, lsi, S):
         "aw": rng.random((N, S, M, L, P), dtype=np.float32),
         "grad_out": rng.standard_normal((N, S, M * D), dtype=np.float32),
     }
-    with Paths(0, 0, 1, 2, 1):
+    with Paths(0, 0, 1, 2, 1, 2):       # tile backward and, where the pyramid fits, the slab forward (it stages ALL S tokens)
         res = run_cabi("f32", x["value"], x["shapes"], x["lsi"], x["loc"], x["aw"], x["grad_out"])
     assert res["bwd_path"] == "bwd_d32_tiles_f32"
+    assert res["fwd_path"] == ("fwd_d32_slab_f32" if S <= 1600 else "fwd_d32_f32")
     check_all(res, oracle(x["value"], x["shapes"], x["lsi"], x["loc"], x["aw"], x["grad_out"]))
+
+
+def test_slab_forward_edges():
+    """The slab forward's share arithmetic: fewer passes than SMs, a last pass with a few queries, one query, and a
+    pyramid at the row limit of the slab."""
+    for N, Lq, levels, seed in ((1, 1, ((5, 6), (3, 3), (2, 2), (1, 1)), 1), (3, 97, ((9, 11), (5, 6), (3, 3), (2, 2)), 2),
+                                (2, 700, ((36, 36), (15, 16), (8, 8), (0, 0)), 3), (1, 130, ((30, 40), (15, 20), (8, 10), (4, 5)), 4)):
+        wl = Workload("slab_edge", N, levels, Lq, loc_dist="uniform")
+        x = np_inputs(wl, seed)
+        with Paths(0, 0, 1, 1, 1, 2):
+            res = run_cabi("f32", x["value"], x["shapes"], x["lsi"], x["loc"], x["aw"], x["grad_out"])
+        assert res["fwd_path"] == "fwd_d32_slab_f32", (levels, res["fwd_path"])
+        check_all(res, oracle(x["value"], x["shapes"], x["lsi"], x["loc"], x["aw"], x["grad_out"]))
 
 
 def test_backward_with_no_value_tokens_writes_zero_gradients():
