@@ -48,6 +48,7 @@ __global__ void __launch_bounds__(256) gather_kernel(const char* table, unsigned
       if (mode == 3) off = (size_t)line * (256 * 1024 + 128);                                              // one line per 256 KB
       if (mode == 4) off = (size_t)line * 1024;                                                            // one line per KB: one head's rows
       if (mode == 5) off = (size_t)line * 1024 + (size_t)group * 128;                                      // ... four heads side by side
+      if (mode == 6) off = (size_t)(__shfl_sync(0xffffffffu, state, 0) >> 8 & line_mask & ~3u) * 128 + (size_t)group * 128;  // 4 ADJACENT lines (512 B) per instruction
       const char* p = base + off + piece * kBytes;
       v[j] = kShared ? Ld<kBytes>::s(p) : Ld<kBytes>::g(p);
     }
@@ -123,6 +124,9 @@ int main() {
   run<16, false, 4>("64 lines at a 1 KB stride (one head)", table, 64, 8, sink, cyc, sms, 0);
   run<16, false, 5>("256 x 4 lines, groups = 4 heads", table, l1_lines, 8, sink, cyc, sms, 0);
   run<16, false, 5>("64 x 4 lines, groups = 4 heads", table, 64, 8, sink, cyc, sms, 0);
+  run<16, false, 6>("L2: 4 adjacent lines (512 B) per instr", table, l2_lines, 8, sink, cyc, sms, 0);
+  run<16, false, 0>("L2: 4 random lines per instr", table, l2_lines, 8, sink, cyc, sms, 0);
+  run<16, false, 6>("L1: 4 adjacent lines per instr", table, l1_lines, 8, sink, cyc, sms, 0);
   printf("== shared-memory loads (32 KB table per CTA)\n");
   run<4, true>("LDS.32  32 lanes/row", table, l1_lines, 32, sink, cyc, sms);
   run<16, true>("LDS.128  8 lanes/row", table, l1_lines, 8, sink, cyc, sms);
