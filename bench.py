@@ -351,6 +351,44 @@ def main():
                "note": "host<->device copies dominate (PCIe); with N GPUs on one host the per-GPU value falls as the "
                        "ranks share the host's pinned-memory / PCIe root bandwidth -- not NCCL, not a kernel"}
         plan.close()
+        # A stream of steps, `depth` in flight (msda_host_pipe_*): what a training loop that prefetches its next batch
+        # does.  Every step's inputs still go up and every step's results still come down inside the timed region (each
+        # slot has its own pinned result buffers); what goes away is the per-call pipeline fill and drain, because the
+        # uploads of step i + 1 overlap the kernels and downloads of step i.
+        try:
+            depth = 3
+            slot_outs = [outs] + [{k: np.empty_like(v) for k, v in outs.items()} for _ in range(depth - 1)]
+            for o in slot_outs[1:]:
+                for v in o.values():
+                    cabi.host_register(v)
+            pipe = cabi.HostPipe(*wl.dims(), device=local_rank, depth=depth)
+
+            def pipe_steps(n):
+                for i in range(n):
+                    o = slot_outs[i % depth]
+                    pipe.submit(i % depth, host["value"], x["shapes"], x["lsi"], host["loc"], host["aw"], host["grad_out"],
+                                o["out"], o["gv"], o["gl"], o["ga"])
+                pipe.wait()
+            pipe_steps(depth + 1)
+            barrier()
+            w0 = time.perf_counter()
+            pipe_steps(e2e_steps)
+            torch.cuda.synchronize()
+            ps = sharding.max_over_ranks([(time.perf_counter() - w0) / e2e_steps], dist, "cuda")[0]
+            same = all(bool(np.array_equal(slot_outs[s]["out"], outs["out"])) for s in range(1, depth))
+            e2e["blocking_call"] = {"value": e2e["value"], "ms_per_step": e2e["ms_per_step"], "api": e2e["api"],
+                                    "note": "one synchronous msda_host_fwd_bwd_f32 call per step (round-1 definition of e2e)"}
+            e2e.update({"value": sharding.aggregate_throughput(wl.items, n_gpus, ps), "ms_per_step": ps * 1e3,
+                        "per_gpu_value": wl.items / ps, "pcie_gbs_per_gpu_each_way": [h2d / ps / 1e9, d2h / ps / 1e9],
+                        "steps_in_flight": depth, "slots_agree": same,
+                        "api": "msda_host_pipe_submit_f32 / msda_host_pipe_wait (C ABI, pinned host buffers in and out, "
+                               f"{depth} steps in flight; every step uploads its inputs and downloads its results)"})
+            pipe.close()
+            for o in slot_outs[1:]:
+                for v in o.values():
+                    cabi.host_unregister(v)
+        except Exception as exc:      # noqa: BLE001
+            e2e["pipelined_error"] = repr(exc)
         # the same call with bf16 storage for the two value-shaped tensors (value up, grad_value down): informational,
         # the contract's e2e above is the fp32 reference-facing call
         try:

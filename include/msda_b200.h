@@ -187,6 +187,29 @@ int msda_host_fwd_bwd_bf16(msda_host_plan *plan, const uint16_t *value, const in
                            const float *attn_weight, const float *grad_output, float *output,
                            uint16_t *grad_value, float *grad_sampling_loc, float *grad_attn_weight);
 
+/* ---- several host-buffer steps in flight ---------------------------------------------------
+ * A pipe is `depth` (1..8) plans that share one set of upload / compute / download streams.
+ * msda_host_pipe_submit_f32 enqueues one forward + backward step on slot `slot` (0 <= slot < depth) and returns without
+ * waiting; msda_host_pipe_wait blocks until that slot's step has landed in the caller's output buffers (slot < 0: every
+ * slot).  A submit on a slot whose previous step is still in flight waits for it first.  Because the streams are
+ * shared, the uploads of step i + 1 overlap the kernels and downloads of step i: a stream of steps (a training loop
+ * that prefetches its next batch) moves at the PCIe rate of large two-way copies instead of paying every step's
+ * pipeline fill and drain.  Buffers must stay valid and untouched until the slot has been waited for; page-locked
+ * buffers (msda_host_register) are required for the copies to be asynchronous at all.  Results are those of
+ * msda_host_fwd_bwd_f32 up to summation order.  (MSDA_B200_PIPE_CHUNKS: query chunks per sample inside a step; default 0 =
+ * the step is one packet: four uploads, one forward + backward over the batch, four downloads.) */
+typedef struct msda_host_pipe msda_host_pipe;
+int msda_host_pipe_create(msda_host_pipe **pipe, int device, int depth,
+                          int batch, int spatial_size, int num_heads, int channels,
+                          int num_levels, int num_query, int num_point);
+void msda_host_pipe_destroy(msda_host_pipe *pipe);
+int msda_host_pipe_submit_f32(msda_host_pipe *pipe, int slot, const float *value, const int64_t *spatial_shapes,
+                              const int64_t *level_start, const float *sampling_loc,
+                              const float *attn_weight, const float *grad_output, float *output,
+                              float *grad_value, float *grad_sampling_loc, float *grad_attn_weight);
+int msda_host_pipe_wait(msda_host_pipe *pipe, int slot);
+int msda_host_pipe_traffic(const msda_host_pipe *pipe, int64_t *h2d_bytes, int64_t *d2h_bytes);
+
 /* ---- tuning / introspection --------------------------------------------------------------
  * Keys: "fwd_path", "bwd_path": 0 = automatic, 1 = force the any-shape kernels (used by bench.py
  * and the tests to exercise every kernel on the same inputs); "bf16_direct_red": 0/1, read by the

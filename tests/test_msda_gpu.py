@@ -8,6 +8,8 @@ gradients rtol 1e-4 (atomic ordering); bf16 rtol 1e-2; with atol = rtol * max|re
 import glob
 import os
 
+import ctypes
+
 import numpy as np
 import pytest
 import torch
@@ -1276,6 +1278,44 @@ def test_layer_stack_graph_replay_against_the_oracle(model):
     assert cabi.launch_count() == n0
     worst = ls.check_against_oracle(layers, frames=1, fwd_rtol=FWD_RTOL, grad_rtol=GRAD_RTOL)
     assert worst["out"] <= FWD_RTOL and worst["grad_value"] <= GRAD_RTOL
+
+
+@pytest.mark.parametrize("chunks", [None, "2"])
+def test_host_pipe_steps_in_flight(chunks, monkeypatch):
+    """msda_host_pipe_*: five steps with different inputs through a pipe of depth 2 (a slot is reused while the other
+    is in flight; pageable AND page-locked buffers), every step against the oracle; the level tables change on the way
+    (the plan caches them)."""
+    if chunks:
+        monkeypatch.setenv("MSDA_B200_PIPE_CHUNKS", chunks)
+    levels_a, levels_b = ((20, 27), (10, 14), (5, 7), (3, 4)), ((27, 20), (14, 10), (7, 5), (4, 3))    # same S
+    S = sum(h * w for h, w in levels_a)
+    pipe = cabi.HostPipe(2, S, 8, 32, 4, 77, 4, depth=2)
+    with pytest.raises(ValueError):
+        pipe.submit(2, *([None] * 10))
+    steps = []
+    for i in range(5):
+        wl = Workload("pipe", 2, levels_b if i == 3 else levels_a, 77, loc_dist="twostage")
+        x = np_inputs(wl, 40 + i)
+        o = {"out": np.full((2, 77, 256), np.nan, np.float32), "gv": np.full(x["value"].shape, np.nan, np.float32),
+             "gl": np.full(x["loc"].shape, np.nan, np.float32), "ga": np.full(x["aw"].shape, np.nan, np.float32)}
+        if i % 2:
+            for a in list(o.values()) + [x[k] for k in ("value", "loc", "aw", "grad_out")]:
+                cabi.host_register(a)
+        steps.append((x, o))
+    for i, (x, o) in enumerate(steps):
+        pipe.submit(i % 2, x["value"], x["shapes"], x["lsi"], x["loc"], x["aw"], x["grad_out"], o["out"], o["gv"], o["gl"], o["ga"])
+    pipe.wait()
+    h2d, d2h = pipe.traffic()
+    assert h2d > 0 and d2h > 0
+    pipe.close()
+    for i, (x, o) in enumerate(steps):
+        if i % 2:
+            for a in list(o.values()) + [x[k] for k in ("value", "loc", "aw", "grad_out")]:
+                cabi.host_unregister(a)
+        ref = oracle(x["value"], x["shapes"], x["lsi"], x["loc"], x["aw"], x["grad_out"])
+        check_all({"out": o["out"], "grad_value": o["gv"], "grad_loc": o["gl"], "grad_aw": o["ga"]}, ref)
+    assert cabi.lib().msda_host_pipe_create(ctypes.byref(ctypes.c_void_p()), 0, 0, 1, 1, 1, 1, 1, 1, 1) == -2   # depth 0
+    assert cabi.lib().msda_host_pipe_create(ctypes.byref(ctypes.c_void_p()), 0, 9, 1, 1, 1, 1, 1, 1, 1) == -2
 
 
 def test_host_plan_bf16_storage_round_trip():

@@ -68,7 +68,8 @@ def both(chunks=1):
 
 
 for name, fn in (("H2D alone", h2d), ("D2H alone", d2h), ("both directions at once", both),
-                 ("both, 16 chunks each", lambda: both(16)), ("both, 64 chunks each", lambda: both(64)),
+                 ("both, 2 chunks each", lambda: both(2)), ("both, 4 chunks each", lambda: both(4)),
+                 ("both, 8 chunks each", lambda: both(8)), ("both, 16 chunks each", lambda: both(16)), ("both, 64 chunks each", lambda: both(64)),
                  ("H2D alone, 16 chunks", lambda: h2d(16)), ("D2H alone, 16 chunks", lambda: d2h(16)),
                  ("both, 16 chunks, 2 streams per direction", lambda: both2(16)),
                  ("both, 64 chunks, 2 streams per direction", lambda: both2(64))):

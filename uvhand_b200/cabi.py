@@ -25,6 +25,8 @@ SYMBOLS = (
     "msda_sample_index_f32",
     "msda_host_plan_create", "msda_host_plan_create_bf16", "msda_host_plan_destroy", "msda_host_plan_traffic",
     "msda_host_register", "msda_host_unregister", "msda_host_fwd_f32", "msda_host_fwd_bwd_f32", "msda_host_fwd_bwd_bf16",
+    "msda_host_pipe_create", "msda_host_pipe_destroy", "msda_host_pipe_submit_f32", "msda_host_pipe_wait",
+    "msda_host_pipe_traffic",
     "msda_b200_set_option", "msda_b200_get_option", "msda_b200_launch_count", "msda_b200_last_path",
 )
 
@@ -68,6 +70,12 @@ def lib() -> ctypes.CDLL:
         L.msda_host_plan_destroy.argtypes = [c_void_p]
         L.msda_host_plan_destroy.restype = None
         L.msda_host_plan_traffic.argtypes = [c_void_p, ctypes.POINTER(c_int64), ctypes.POINTER(c_int64)]
+        L.msda_host_pipe_create.argtypes = [ctypes.POINTER(c_void_p), c_int, c_int] + [c_int] * 7
+        L.msda_host_pipe_destroy.argtypes = [c_void_p]
+        L.msda_host_pipe_destroy.restype = None
+        L.msda_host_pipe_submit_f32.argtypes = [c_void_p, c_int] + [c_void_p] * 10
+        L.msda_host_pipe_wait.argtypes = [c_void_p, c_int]
+        L.msda_host_pipe_traffic.argtypes = [c_void_p, ctypes.POINTER(c_int64), ctypes.POINTER(c_int64)]
         L.msda_host_register.argtypes = [c_void_p, c_int64]
         L.msda_host_unregister.argtypes = [c_void_p]
         L.msda_host_fwd_f32.argtypes = [c_void_p] * 7
@@ -210,6 +218,52 @@ class HostPlan:
         check(fn(self._h, self._p(value), self._p(shapes), self._p(lsi), self._p(loc),
                                           self._p(aw), self._p(grad_out), self._p(out), self._p(gv),
                                           self._p(gl), self._p(ga)), "msda_host_fwd_bwd_f32")
+
+
+class HostPipe(HostPlan):
+    """`depth` host-buffer steps in flight on one device (msda_host_pipe_*): submit() returns once a step is enqueued,
+    wait() once its results are in the caller's arrays.  The arrays of a slot must not be touched between the two."""
+
+    def __init__(self, N, S, M, D, L, Lq, P, device: int = 0, depth: int = 2):
+        self.dims = (N, S, M, D, L, Lq, P)
+        self.value_bf16 = False
+        self.depth = int(depth)
+        self._h = c_void_p()
+        self._keep = [None] * self.depth          # the arrays of a step in flight must outlive it
+        check(lib().msda_host_pipe_create(ctypes.byref(self._h), device, self.depth, *self.dims), "msda_host_pipe_create")
+
+    def close(self):
+        if self._h:
+            lib().msda_host_pipe_destroy(self._h)
+            self._h = c_void_p()
+            self._keep = [None] * self.depth
+
+    def traffic(self):
+        a, b = c_int64(0), c_int64(0)
+        check(lib().msda_host_pipe_traffic(self._h, ctypes.byref(a), ctypes.byref(b)), "msda_host_pipe_traffic")
+        return a.value, b.value
+
+    def submit(self, slot, value, shapes, lsi, loc, aw, grad_out, out, gv, gl, ga):
+        if not 0 <= slot < self.depth:
+            raise ValueError(f"HostPipe: slot {slot} outside [0, {self.depth})")
+        self._validate(value=value, shapes=shapes, lsi=lsi, loc=loc, aw=aw, grad_out=grad_out, out=out, gv=gv, gl=gl,
+                       ga=ga)
+        check(lib().msda_host_pipe_submit_f32(self._h, slot, self._p(value), self._p(shapes), self._p(lsi), self._p(loc),
+                                              self._p(aw), self._p(grad_out), self._p(out), self._p(gv), self._p(gl),
+                                              self._p(ga)), "msda_host_pipe_submit_f32")
+        self._keep[slot] = (value, shapes, lsi, loc, aw, grad_out, out, gv, gl, ga)
+
+    def wait(self, slot: int = -1):
+        check(lib().msda_host_pipe_wait(self._h, slot), "msda_host_pipe_wait")
+        for i in (range(self.depth) if slot < 0 else (slot,)):
+            self._keep[i] = None
+
+    def forward(self, *a, **k):
+        raise NotImplementedError("HostPipe runs forward + backward steps; use HostPlan.forward")
+
+    def forward_backward(self, *a):
+        self.submit(0, *a)
+        self.wait(0)
 
 
 def host_register(arr) -> None:

@@ -716,6 +716,13 @@ struct msda_host_plan {
   cudaEvent_t* ev_value;        // [N] value[b] on the device
   cudaEvent_t ev_tables;
   cudaEvent_t* ev_out;          // [N * n_chunks + N] trace only: chunk results / grad_value[b] on the host
+  int64_t h_tables[3 * 64];     // spatial_shapes + level_start_index as last uploaded: a step with the same level tables
+  int tables_valid;             // (every step of a training run) skips the two small uploads
+  int whole_batch;              // a pipe slot with MSDA_B200_PIPE_CHUNKS=0 (default): the step is ONE packet -- four
+                                // uploads, one forward + backward over all samples, four downloads (steps overlap each
+                                // other, so nothing inside a step needs to; large copies run at the best two-way rate)
+  int owns_streams;             // 0: a slot of a msda_host_pipe, its streams belong to the pipe's first slot
+  cudaEvent_t ev_done;          // asynchronous use (msda_host_pipe): everything of the last submitted step has landed
   int ramp;                     // MSDA_B200_HOST_RAMP=1: growing chunks in the first sample (measured: no gain)
   int trace;                    // MSDA_B200_HOST_TRACE=1: print the timeline of every call to stderr
 };
@@ -727,7 +734,7 @@ struct msda_host_plan {
   } while (0)
 
 static int plan_create(msda_host_plan** out_plan, int device, int N, int S, int M, int D, int L, int Lq, int P,
-                       int value_bf16);
+                       int value_bf16, const msda_host_plan* share = nullptr, int chunks = 0);
 
 int msda_host_plan_create(msda_host_plan** out_plan, int device, int N, int S, int M, int D, int L,
                           int Lq, int P) {
@@ -741,7 +748,7 @@ int msda_host_plan_create_bf16(msda_host_plan** out_plan, int device, int N, int
 }
 
 static int plan_create(msda_host_plan** out_plan, int device, int N, int S, int M, int D, int L, int Lq, int P,
-                       int value_bf16) {
+                       int value_bf16, const msda_host_plan* share, int chunks) {
   if (!out_plan) return MSDA_ERR_NULL_POINTER;
   *out_plan = nullptr;
   int rc = check_dims(N, S, M, D, L, Lq, P);
@@ -775,12 +782,20 @@ static int plan_create(msda_host_plan** out_plan, int device, int N, int S, int 
       const long long v = atoll(env);
       if (v >= 1 && v <= 256) c = v;
     }
+    if (chunks > 0) c = chunks;                                // a pipe's slots: steps overlap each other instead
     if (c > Lq) c = Lq > 0 ? Lq : 1;
     pl->n_chunks = (int)c;
   }
-  cudaError_t e = cudaStreamCreateWithFlags(&pl->s_in, cudaStreamNonBlocking);
-  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&pl->s_run, cudaStreamNonBlocking);
-  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&pl->s_out, cudaStreamNonBlocking);
+  cudaError_t e = cudaSuccess;
+  pl->owns_streams = share == nullptr;
+  if (share) {
+    pl->s_in = share->s_in; pl->s_run = share->s_run; pl->s_out = share->s_out;
+  } else {
+    e = cudaStreamCreateWithFlags(&pl->s_in, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&pl->s_run, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&pl->s_out, cudaStreamNonBlocking);
+  }
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&pl->ev_done, cudaEventDisableTiming);
   const int n_ev = (N > 0 ? N : 1) * pl->n_chunks;
   pl->trace = getenv("MSDA_B200_HOST_TRACE") != nullptr;
   pl->ramp = 0;
@@ -848,9 +863,12 @@ void msda_host_plan_destroy(msda_host_plan* pl) {
   }
   delete[] pl->ev_in; delete[] pl->ev_run; delete[] pl->ev_value;
   if (pl->ev_tables) cudaEventDestroy(pl->ev_tables);
-  if (pl->s_in) cudaStreamDestroy(pl->s_in);
-  if (pl->s_run) cudaStreamDestroy(pl->s_run);
-  if (pl->s_out) cudaStreamDestroy(pl->s_out);
+  if (pl->ev_done) cudaEventDestroy(pl->ev_done);
+  if (pl->owns_streams) {
+    if (pl->s_in) cudaStreamDestroy(pl->s_in);
+    if (pl->s_run) cudaStreamDestroy(pl->s_run);
+    if (pl->s_out) cudaStreamDestroy(pl->s_out);
+  }
   delete pl;
 }
 
@@ -894,7 +912,7 @@ static cudaError_t copy_batch(void** dsts, void** srcs, size_t* sizes, int n, cu
 // cross-query or cross-sample term), so nothing but pointer offsets is needed.
 static int host_pipeline(msda_host_plan* pl, const void* value_any, const int64_t* shapes, const int64_t* lsi,
                          const float* loc, const float* aw, const float* go, float* out, void* gv_any,
-                         float* gl, float* ga) {
+                         float* gl, float* ga, bool blocking = true) {
   const bool b16 = pl->value_bf16 != 0;
   const size_t vsz = b16 ? 2 : 4;
   const char* value = static_cast<const char*>(value_any);
@@ -906,11 +924,51 @@ static int host_pipeline(msda_host_plan* pl, const void* value_any, const int64_
   const size_t v_per = (size_t)S * M * D;
   const size_t o_per_q = (size_t)M * D, a_per_q = (size_t)M * L * P;
   const cudaMemcpyKind H2D = cudaMemcpyHostToDevice, D2H = cudaMemcpyDeviceToHost;
-  MSDA_CUDA_TRY(cudaMemcpyAsync(pl->d_shapes, shapes, sizeof(int64_t) * 2 * L, H2D, pl->s_in));
-  MSDA_CUDA_TRY(cudaMemcpyAsync(pl->d_lsi, lsi, sizeof(int64_t) * L, H2D, pl->s_in));
+  {
+    // the level tables are read from the CALLER's arrays right now (they may be pageable and change after we return)
+    const bool cacheable = L <= 64;
+    if (!(cacheable && pl->tables_valid && !memcmp(pl->h_tables, shapes, sizeof(int64_t) * 2 * L) &&
+          !memcmp(pl->h_tables + 2 * L, lsi, sizeof(int64_t) * L))) {
+      MSDA_CUDA_TRY(cudaMemcpyAsync(pl->d_shapes, shapes, sizeof(int64_t) * 2 * L, H2D, pl->s_in));
+      MSDA_CUDA_TRY(cudaMemcpyAsync(pl->d_lsi, lsi, sizeof(int64_t) * L, H2D, pl->s_in));
+      pl->tables_valid = 0;
+      if (cacheable) {
+        memcpy(pl->h_tables, shapes, sizeof(int64_t) * 2 * L);
+        memcpy(pl->h_tables + 2 * L, lsi, sizeof(int64_t) * L);
+        pl->tables_valid = 1;
+      }
+    }
+  }
   MSDA_CUDA_TRY(cudaEventRecord(pl->ev_tables, pl->s_in));
   MSDA_CUDA_TRY(cudaStreamWaitEvent(pl->s_run, pl->ev_tables, 0));
   if (bwd && pl->n_value) MSDA_CUDA_TRY(cudaMemsetAsync(pl->d_gv, 0, sizeof(float) * pl->n_value, pl->s_run));
+  if (pl->whole_batch && !b16 && bwd) {
+    if (pl->n_value) MSDA_CUDA_TRY(cudaMemcpyAsync(pl->d_value, value, sizeof(float) * pl->n_value, H2D, pl->s_in));
+    if (pl->n_loc) MSDA_CUDA_TRY(cudaMemcpyAsync(pl->d_loc, loc, sizeof(float) * pl->n_loc, H2D, pl->s_in));
+    if (pl->n_aw) MSDA_CUDA_TRY(cudaMemcpyAsync(pl->d_aw, aw, sizeof(float) * pl->n_aw, H2D, pl->s_in));
+    if (pl->n_out) MSDA_CUDA_TRY(cudaMemcpyAsync(pl->d_go, go, sizeof(float) * pl->n_out, H2D, pl->s_in));
+    MSDA_CUDA_TRY(cudaEventRecord(pl->ev_in[0], pl->s_in));
+    MSDA_CUDA_TRY(cudaStreamWaitEvent(pl->s_run, pl->ev_in[0], 0));
+    if (Lq > 0) {
+      int rc = msda_fwd_f32(pl->d_value, pl->d_shapes, pl->d_lsi, pl->d_loc, pl->d_aw, N, S, M, D, L, Lq, P, pl->d_out, pl->s_run);
+      if (rc) return rc;
+      rc = msda_bwd_f32(pl->d_go, pl->d_value, pl->d_shapes, pl->d_lsi, pl->d_loc, pl->d_aw, N, S, M, D, L, Lq, P, pl->d_gv,
+                        pl->d_gl, pl->d_ga, pl->s_run);
+      if (rc) return rc;
+    }
+    MSDA_CUDA_TRY(cudaEventRecord(pl->ev_run[0], pl->s_run));
+    MSDA_CUDA_TRY(cudaStreamWaitEvent(pl->s_out, pl->ev_run[0], 0));
+    if (pl->n_out) MSDA_CUDA_TRY(cudaMemcpyAsync(out, pl->d_out, sizeof(float) * pl->n_out, D2H, pl->s_out));
+    if (pl->n_loc) MSDA_CUDA_TRY(cudaMemcpyAsync(gl, pl->d_gl, sizeof(float) * pl->n_loc, D2H, pl->s_out));
+    if (pl->n_aw) MSDA_CUDA_TRY(cudaMemcpyAsync(ga, pl->d_ga, sizeof(float) * pl->n_aw, D2H, pl->s_out));
+    if (pl->n_value) MSDA_CUDA_TRY(cudaMemcpyAsync(gv, pl->d_gv, sizeof(float) * pl->n_value, D2H, pl->s_out));
+    if (!blocking) {
+      MSDA_CUDA_TRY(cudaEventRecord(pl->ev_done, pl->s_out));
+      return MSDA_OK;
+    }
+    MSDA_CUDA_TRY(cudaStreamSynchronize(pl->s_out));
+    return MSDA_OK;
+  }
   for (int b = 0; b < N; ++b) {
     if (v_per) MSDA_CUDA_TRY(cudaMemcpyAsync(d_value + b * v_per * vsz, value + b * v_per * vsz, vsz * v_per, H2D, pl->s_in));
     MSDA_CUDA_TRY(cudaEventRecord(pl->ev_value[b], pl->s_in));
@@ -990,6 +1048,11 @@ static int host_pipeline(msda_host_plan* pl, const void* value_any, const int64_
     }
     if (pl->trace && pl->ev_out) cudaEventRecord(pl->ev_out[N * pl->n_chunks + b], pl->s_out);
   }
+  if (!blocking) {
+    // the download stream has waited for every kernel, and every kernel for its uploads: its tail is the step's end
+    MSDA_CUDA_TRY(cudaEventRecord(pl->ev_done, pl->s_out));
+    return MSDA_OK;
+  }
   MSDA_CUDA_TRY(cudaStreamSynchronize(pl->s_out));
   MSDA_CUDA_TRY(cudaStreamSynchronize(pl->s_run));
   MSDA_CUDA_TRY(cudaStreamSynchronize(pl->s_in));
@@ -1011,6 +1074,7 @@ static int host_pipeline(msda_host_plan* pl, const void* value_any, const int64_
 // On failure nothing may still be reading or writing the caller's buffers when we return.
 static int host_finish(msda_host_plan* pl, int rc) {
   if (rc != MSDA_OK) {
+    pl->tables_valid = 0;
     cudaStreamSynchronize(pl->s_in);
     cudaStreamSynchronize(pl->s_run);
     cudaStreamSynchronize(pl->s_out);
@@ -1045,6 +1109,86 @@ int msda_host_fwd_bwd_bf16(msda_host_plan* pl, const uint16_t* value, const int6
   if (!pl->value_bf16) return MSDA_ERR_UNSUPPORTED;
   MSDA_CUDA_TRY(cudaSetDevice(pl->device));
   return host_finish(pl, host_pipeline(pl, value, shapes, lsi, loc, aw, go, out, gv, gl, ga));
+}
+
+// ---- several steps in flight -----------------------------------------------------------------------------------
+// A pipe is `depth` plans (device buffers, events) on ONE set of three streams.  submit() enqueues a whole step and
+// returns; because the streams are shared, the uploads of step i + 1 run while step i computes and downloads, so a
+// stream of steps moves at the PCIe rate of large two-way copies instead of paying every step's fill and drain.
+struct msda_host_pipe {
+  int depth;
+  msda_host_plan* slot[8];
+  int pending[8];
+};
+void msda_host_pipe_destroy(msda_host_pipe* pp);
+
+int msda_host_pipe_create(msda_host_pipe** out_pipe, int device, int depth, int N, int S, int M, int D, int L,
+                          int Lq, int P) {
+  if (!out_pipe) return MSDA_ERR_NULL_POINTER;
+  *out_pipe = nullptr;
+  if (depth < 1 || depth > 8) return MSDA_ERR_BAD_DIMS;
+  msda_host_pipe* pp = new (std::nothrow) msda_host_pipe();
+  if (!pp) return (int)cudaErrorMemoryAllocation;
+  memset(pp, 0, sizeof(*pp));
+  pp->depth = depth;
+  int chunks = 0;      // 0: the whole step is one packet (steps overlap each other, so the copies can stay large)
+  if (const char* env = getenv("MSDA_B200_PIPE_CHUNKS")) {   // >= 1: query chunks per sample inside a step, as in a plan
+    const int v = atoi(env);
+    if (v >= 0 && v <= 256) chunks = v;
+  }
+  for (int i = 0; i < depth; ++i) {
+    const int rc = plan_create(&pp->slot[i], device, N, S, M, D, L, Lq, P, 0, i ? pp->slot[0] : nullptr, chunks ? chunks : 1);
+    if (rc) {
+      msda_host_pipe_destroy(pp);
+      return rc;
+    }
+    pp->slot[i]->whole_batch = chunks == 0;
+  }
+  *out_pipe = pp;
+  return MSDA_OK;
+}
+
+void msda_host_pipe_destroy(msda_host_pipe* pp) {
+  if (!pp) return;
+  if (pp->slot[0]) {
+    cudaSetDevice(pp->slot[0]->device);
+    cudaStreamSynchronize(pp->slot[0]->s_in);
+    cudaStreamSynchronize(pp->slot[0]->s_run);
+    cudaStreamSynchronize(pp->slot[0]->s_out);
+  }
+  for (int i = pp->depth - 1; i >= 0; --i) msda_host_plan_destroy(pp->slot[i]);   // slot 0 (the streams' owner) last
+  delete pp;
+}
+
+int msda_host_pipe_wait(msda_host_pipe* pp, int slot) {
+  if (!pp) return MSDA_ERR_NULL_POINTER;
+  if (slot >= pp->depth) return MSDA_ERR_BAD_DIMS;
+  for (int i = slot < 0 ? 0 : slot; i < (slot < 0 ? pp->depth : slot + 1); ++i) {
+    if (!pp->pending[i]) continue;
+    MSDA_CUDA_TRY(cudaSetDevice(pp->slot[i]->device));
+    MSDA_CUDA_TRY(cudaEventSynchronize(pp->slot[i]->ev_done));
+    pp->pending[i] = 0;
+  }
+  return MSDA_OK;
+}
+
+int msda_host_pipe_submit_f32(msda_host_pipe* pp, int slot, const float* value, const int64_t* shapes, const int64_t* lsi,
+                              const float* loc, const float* aw, const float* go, float* out, float* gv, float* gl,
+                              float* ga) {
+  if (!pp || !value || !shapes || !lsi || !loc || !aw || !go || !out || !gv || !gl || !ga) return MSDA_ERR_NULL_POINTER;
+  if (slot < 0 || slot >= pp->depth) return MSDA_ERR_BAD_DIMS;
+  int rc = msda_host_pipe_wait(pp, slot);     // the slot's device buffers are free once its previous step has landed
+  if (rc) return rc;
+  msda_host_plan* pl = pp->slot[slot];
+  MSDA_CUDA_TRY(cudaSetDevice(pl->device));
+  rc = host_finish(pl, host_pipeline(pl, value, shapes, lsi, loc, aw, go, out, gv, gl, ga, false));
+  if (rc == MSDA_OK) pp->pending[slot] = 1;
+  return rc;
+}
+
+int msda_host_pipe_traffic(const msda_host_pipe* pp, int64_t* h2d, int64_t* d2h) {
+  if (!pp || !pp->slot[0]) return MSDA_ERR_NULL_POINTER;
+  return msda_host_plan_traffic(pp->slot[0], h2d, d2h);
 }
 
 }  // extern "C"
