@@ -195,7 +195,8 @@ int msda_host_fwd_bwd_bf16(msda_host_plan *plan, const uint16_t *value, const in
  * shared, the uploads of step i + 1 overlap the kernels and downloads of step i: a stream of steps (a training loop
  * that prefetches its next batch) moves at the PCIe rate of large two-way copies instead of paying every step's
  * pipeline fill and drain.  Buffers must stay valid and untouched until the slot has been waited for; page-locked
- * buffers (msda_host_register) are required for the copies to be asynchronous at all.  Results are those of
+ * buffers (msda_host_register) are required for the copies to be asynchronous at all.  One host thread drives a pipe
+ * (like a plan, it is not thread-safe); use one pipe per thread or device.  Results are those of
  * msda_host_fwd_bwd_f32 up to summation order.  (MSDA_B200_PIPE_CHUNKS: query chunks per sample inside a step; default 0 =
  * the step is one packet: four uploads, one forward + backward over the batch, four downloads.) */
 typedef struct msda_host_pipe msda_host_pipe;
