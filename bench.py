@@ -414,6 +414,38 @@ def main():
                                          "h2d_bytes_per_step": h2d16, "d2h_bytes_per_step": d2h16,
                                          "api": "msda_host_fwd_bwd_bf16 (value / grad_value travel as bf16; 1e-2 tolerance mode)"}
             plan16.close()
+            # ... and as a stream of steps (three in flight), like e2e.value
+            depth16 = 3
+            gv16s = [gv16] + [np.empty_like(gv16) for _ in range(depth16 - 1)]
+            o16 = [outs] + [{k: np.empty_like(v) for k, v in outs.items() if k != "gv"} for _ in range(depth16 - 1)]
+            for g in gv16s[1:]:
+                cabi.host_register(g)
+            for o in o16[1:]:
+                for v in o.values():
+                    cabi.host_register(v)
+            pipe16 = cabi.HostPipe(*wl.dims(), device=local_rank, depth=depth16, value_bf16=True)
+
+            def pipe16_steps(n):
+                for i in range(n):
+                    o = o16[i % depth16]
+                    pipe16.submit(i % depth16, v16, x["shapes"], x["lsi"], host["loc"], host["aw"], host["grad_out"],
+                                  o["out"], gv16s[i % depth16], o["gl"], o["ga"])
+                pipe16.wait()
+            pipe16_steps(depth16 + 1)
+            barrier()
+            w0 = time.perf_counter()
+            pipe16_steps(e2e_steps)
+            torch.cuda.synchronize()
+            p16 = sharding.max_over_ranks([(time.perf_counter() - w0) / e2e_steps], dist, "cuda")[0]
+            e2e["bf16_value_storage"]["steps_in_flight"] = {"value": sharding.aggregate_throughput(wl.items, n_gpus, p16),
+                                                            "ms_per_step": p16 * 1e3, "depth": depth16,
+                                                            "api": "msda_host_pipe_submit_bf16 / msda_host_pipe_wait"}
+            pipe16.close()
+            for g in gv16s[1:]:
+                cabi.host_unregister(g)
+            for o in o16[1:]:
+                for v in o.values():
+                    cabi.host_unregister(v)
             cabi.host_unregister(v16)
             cabi.host_unregister(gv16)
         except Exception as exc:      # noqa: BLE001

@@ -208,6 +208,14 @@ int msda_host_pipe_submit_f32(msda_host_pipe *pipe, int slot, const float *value
                               const int64_t *level_start, const float *sampling_loc,
                               const float *attn_weight, const float *grad_output, float *output,
                               float *grad_value, float *grad_sampling_loc, float *grad_attn_weight);
+/* The same with value / grad_value travelling as bf16 (see msda_host_plan_create_bf16); a pipe is either fp32 or bf16. */
+int msda_host_pipe_create_bf16(msda_host_pipe **pipe, int device, int depth,
+                               int batch, int spatial_size, int num_heads, int channels,
+                               int num_levels, int num_query, int num_point);
+int msda_host_pipe_submit_bf16(msda_host_pipe *pipe, int slot, const uint16_t *value, const int64_t *spatial_shapes,
+                               const int64_t *level_start, const float *sampling_loc,
+                               const float *attn_weight, const float *grad_output, float *output,
+                               uint16_t *grad_value, float *grad_sampling_loc, float *grad_attn_weight);
 int msda_host_pipe_wait(msda_host_pipe *pipe, int slot);
 int msda_host_pipe_traffic(const msda_host_pipe *pipe, int64_t *h2d_bytes, int64_t *d2h_bytes);
 

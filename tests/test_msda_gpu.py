@@ -1318,6 +1318,34 @@ def test_host_pipe_steps_in_flight(chunks, monkeypatch):
     assert cabi.lib().msda_host_pipe_create(ctypes.byref(ctypes.c_void_p()), 0, 9, 1, 1, 1, 1, 1, 1, 1) == -2
 
 
+def test_host_pipe_bf16_storage():
+    """msda_host_pipe_*_bf16: three steps in flight with value / grad_value as bf16 bit patterns, against the oracle on the
+    rounded value; an fp32 submit on a bf16 pipe is rejected."""
+    wl = Workload("p16", 2, ((20, 27), (10, 14), (5, 7), (3, 4)), 150, loc_dist="twostage")
+    pipe = cabi.HostPipe(*wl.dims(), depth=3, value_bf16=True)
+    steps = []
+    for i in range(3):
+        x = np_inputs(wl, 50 + i)
+        v16 = torch.from_numpy(x["value"]).to(torch.bfloat16)
+        o = {"out": np.full((wl.N, wl.Lq, wl.M * wl.D), np.nan, np.float32), "gv": np.zeros(x["value"].shape, np.uint16),
+             "gl": np.full(x["loc"].shape, np.nan, np.float32), "ga": np.full(x["aw"].shape, np.nan, np.float32)}
+        steps.append((x, v16.view(torch.int16).numpy().view(np.uint16).copy(), v16.float().numpy(), o))
+    for i, (x, bits, _, o) in enumerate(steps):
+        pipe.submit(i, bits, x["shapes"], x["lsi"], x["loc"], x["aw"], x["grad_out"], o["out"], o["gv"], o["gl"], o["ga"])
+    pipe.wait()
+    x, bits, _, o = steps[0]
+    rc = cabi.lib().msda_host_pipe_submit_f32(pipe._h, 0, *[a.ctypes.data_as(ctypes.c_void_p) for a in (
+        x["value"], x["shapes"], x["lsi"], x["loc"], x["aw"], x["grad_out"], o["out"], x["value"].copy(), o["gl"], o["ga"])])
+    assert rc == -4                                        # MSDA_ERR_UNSUPPORTED
+    pipe.close()
+    for x, _, v_round, o in steps:
+        ref = oracle(v_round, x["shapes"], x["lsi"], x["loc"], x["aw"], x["grad_out"])
+        close(o["out"], ref["out"], FWD_RTOL)
+        close(o["gl"], ref["grad_loc"], GRAD_RTOL)
+        close(o["ga"], ref["grad_aw"], GRAD_RTOL)
+        close(torch.from_numpy(o["gv"].view(np.int16)).view(torch.bfloat16).float().numpy(), ref["grad_value"], BF16_RTOL)
+
+
 def test_host_plan_bf16_storage_round_trip():
     """msda_host_fwd_bwd_bf16: value up / grad_value down as bf16 (fp32 accumulation on the device, one rounding),
     everything else fp32, against the oracle run on the bf16-rounded value."""

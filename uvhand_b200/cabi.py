@@ -25,7 +25,8 @@ SYMBOLS = (
     "msda_sample_index_f32",
     "msda_host_plan_create", "msda_host_plan_create_bf16", "msda_host_plan_destroy", "msda_host_plan_traffic",
     "msda_host_register", "msda_host_unregister", "msda_host_fwd_f32", "msda_host_fwd_bwd_f32", "msda_host_fwd_bwd_bf16",
-    "msda_host_pipe_create", "msda_host_pipe_destroy", "msda_host_pipe_submit_f32", "msda_host_pipe_wait",
+    "msda_host_pipe_create", "msda_host_pipe_create_bf16", "msda_host_pipe_destroy", "msda_host_pipe_submit_f32",
+    "msda_host_pipe_submit_bf16", "msda_host_pipe_wait",
     "msda_host_pipe_traffic",
     "msda_b200_set_option", "msda_b200_get_option", "msda_b200_launch_count", "msda_b200_last_path",
 )
@@ -73,7 +74,9 @@ def lib() -> ctypes.CDLL:
         L.msda_host_pipe_create.argtypes = [ctypes.POINTER(c_void_p), c_int, c_int] + [c_int] * 7
         L.msda_host_pipe_destroy.argtypes = [c_void_p]
         L.msda_host_pipe_destroy.restype = None
+        L.msda_host_pipe_create_bf16.argtypes = [ctypes.POINTER(c_void_p), c_int, c_int] + [c_int] * 7
         L.msda_host_pipe_submit_f32.argtypes = [c_void_p, c_int] + [c_void_p] * 10
+        L.msda_host_pipe_submit_bf16.argtypes = [c_void_p, c_int] + [c_void_p] * 10
         L.msda_host_pipe_wait.argtypes = [c_void_p, c_int]
         L.msda_host_pipe_traffic.argtypes = [c_void_p, ctypes.POINTER(c_int64), ctypes.POINTER(c_int64)]
         L.msda_host_register.argtypes = [c_void_p, c_int64]
@@ -224,13 +227,14 @@ class HostPipe(HostPlan):
     """`depth` host-buffer steps in flight on one device (msda_host_pipe_*): submit() returns once a step is enqueued,
     wait() once its results are in the caller's arrays.  The arrays of a slot must not be touched between the two."""
 
-    def __init__(self, N, S, M, D, L, Lq, P, device: int = 0, depth: int = 2):
+    def __init__(self, N, S, M, D, L, Lq, P, device: int = 0, depth: int = 2, value_bf16: bool = False):
         self.dims = (N, S, M, D, L, Lq, P)
-        self.value_bf16 = False
+        self.value_bf16 = bool(value_bf16)
         self.depth = int(depth)
         self._h = c_void_p()
         self._keep = [None] * self.depth          # the arrays of a step in flight must outlive it
-        check(lib().msda_host_pipe_create(ctypes.byref(self._h), device, self.depth, *self.dims), "msda_host_pipe_create")
+        create = lib().msda_host_pipe_create_bf16 if self.value_bf16 else lib().msda_host_pipe_create
+        check(create(ctypes.byref(self._h), device, self.depth, *self.dims), "msda_host_pipe_create")
 
     def close(self):
         if self._h:
@@ -248,9 +252,9 @@ class HostPipe(HostPlan):
             raise ValueError(f"HostPipe: slot {slot} outside [0, {self.depth})")
         self._validate(value=value, shapes=shapes, lsi=lsi, loc=loc, aw=aw, grad_out=grad_out, out=out, gv=gv, gl=gl,
                        ga=ga)
-        check(lib().msda_host_pipe_submit_f32(self._h, slot, self._p(value), self._p(shapes), self._p(lsi), self._p(loc),
-                                              self._p(aw), self._p(grad_out), self._p(out), self._p(gv), self._p(gl),
-                                              self._p(ga)), "msda_host_pipe_submit_f32")
+        fn = lib().msda_host_pipe_submit_bf16 if self.value_bf16 else lib().msda_host_pipe_submit_f32
+        check(fn(self._h, slot, self._p(value), self._p(shapes), self._p(lsi), self._p(loc), self._p(aw), self._p(grad_out),
+                 self._p(out), self._p(gv), self._p(gl), self._p(ga)), "msda_host_pipe_submit")
         self._keep[slot] = (value, shapes, lsi, loc, aw, grad_out, out, gv, gl, ga)
 
     def wait(self, slot: int = -1):

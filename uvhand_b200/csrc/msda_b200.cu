@@ -1122,8 +1122,22 @@ struct msda_host_pipe {
 };
 void msda_host_pipe_destroy(msda_host_pipe* pp);
 
+static int pipe_create(msda_host_pipe** out_pipe, int device, int depth, int N, int S, int M, int D, int L, int Lq, int P,
+                       int value_bf16);
+
 int msda_host_pipe_create(msda_host_pipe** out_pipe, int device, int depth, int N, int S, int M, int D, int L,
                           int Lq, int P) {
+  return pipe_create(out_pipe, device, depth, N, S, M, D, L, Lq, P, 0);
+}
+
+int msda_host_pipe_create_bf16(msda_host_pipe** out_pipe, int device, int depth, int N, int S, int M, int D, int L,
+                               int Lq, int P) {
+  if (!d32_eligible(S > 0 ? S : 1, M > 0 ? M : 1, D, L > 0 ? L : 1, P > 0 ? P : 1)) return MSDA_ERR_UNSUPPORTED;
+  return pipe_create(out_pipe, device, depth, N, S, M, D, L, Lq, P, 1);
+}
+
+static int pipe_create(msda_host_pipe** out_pipe, int device, int depth, int N, int S, int M, int D, int L, int Lq, int P,
+                       int value_bf16) {
   if (!out_pipe) return MSDA_ERR_NULL_POINTER;
   *out_pipe = nullptr;
   if (depth < 1 || depth > 8) return MSDA_ERR_BAD_DIMS;
@@ -1137,7 +1151,7 @@ int msda_host_pipe_create(msda_host_pipe** out_pipe, int device, int depth, int 
     if (v >= 0 && v <= 256) chunks = v;
   }
   for (int i = 0; i < depth; ++i) {
-    const int rc = plan_create(&pp->slot[i], device, N, S, M, D, L, Lq, P, 0, i ? pp->slot[0] : nullptr, chunks ? chunks : 1);
+    const int rc = plan_create(&pp->slot[i], device, N, S, M, D, L, Lq, P, value_bf16, i ? pp->slot[0] : nullptr, chunks ? chunks : 1);
     if (rc) {
       msda_host_pipe_destroy(pp);
       return rc;
@@ -1177,7 +1191,23 @@ int msda_host_pipe_submit_f32(msda_host_pipe* pp, int slot, const float* value, 
                               float* ga) {
   if (!pp || !value || !shapes || !lsi || !loc || !aw || !go || !out || !gv || !gl || !ga) return MSDA_ERR_NULL_POINTER;
   if (slot < 0 || slot >= pp->depth) return MSDA_ERR_BAD_DIMS;
+  if (pp->slot[slot]->value_bf16) return MSDA_ERR_UNSUPPORTED;
   int rc = msda_host_pipe_wait(pp, slot);     // the slot's device buffers are free once its previous step has landed
+  if (rc) return rc;
+  msda_host_plan* pl = pp->slot[slot];
+  MSDA_CUDA_TRY(cudaSetDevice(pl->device));
+  rc = host_finish(pl, host_pipeline(pl, value, shapes, lsi, loc, aw, go, out, gv, gl, ga, false));
+  if (rc == MSDA_OK) pp->pending[slot] = 1;
+  return rc;
+}
+
+int msda_host_pipe_submit_bf16(msda_host_pipe* pp, int slot, const uint16_t* value, const int64_t* shapes,
+                               const int64_t* lsi, const float* loc, const float* aw, const float* go, float* out,
+                               uint16_t* gv, float* gl, float* ga) {
+  if (!pp || !value || !shapes || !lsi || !loc || !aw || !go || !out || !gv || !gl || !ga) return MSDA_ERR_NULL_POINTER;
+  if (slot < 0 || slot >= pp->depth) return MSDA_ERR_BAD_DIMS;
+  if (!pp->slot[slot]->value_bf16) return MSDA_ERR_UNSUPPORTED;
+  int rc = msda_host_pipe_wait(pp, slot);
   if (rc) return rc;
   msda_host_plan* pl = pp->slot[slot];
   MSDA_CUDA_TRY(cudaSetDevice(pl->device));
