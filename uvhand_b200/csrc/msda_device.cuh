@@ -130,6 +130,11 @@ struct Chunk<float> {
     const float f = __uint_as_float(0x3f800000u | ((unsigned)(size_t)p & 0xffffu));
     return make_float4(f, f, f, f);
 #endif
+#ifdef MSDA_EXPERIMENT_VALUE_NO_ALLOCATE   // timing experiment: gathered rows do not allocate in L1 either
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+#endif
     return __ldg(p);
   }
   // red.global.add.v4.f32: one 16 B reduction instead of four scalar atomics (sm_90+).
